@@ -1,0 +1,229 @@
+/*
+ * t2h.h — C ABI of libt2h.so, the B200 (sm_100a) kernel library under the
+ * Text2Human hot path (hierarchical VQGAN encode/quantize/decode + the
+ * index-prediction transformer).
+ *
+ * The reference (yumingj/Text2Human) is pure Python/PyTorch and has no FFI of
+ * its own: its boundary is the nn.Module API of
+ * models/archs/vqgan_arch.py and models/archs/transformer_arch.py.  This header
+ * is the seam *beneath* the Python classes in text2human_b200/ that mirror
+ * those modules; every entry point names the reference call(s) it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative T2H_E* code otherwise;
+ *     t2h_last_error() returns a thread-local human-readable message.
+ *   - functions never allocate device memory, never synchronise and never
+ *     throw; all device pointers are caller-owned; `stream` is a cudaStream_t.
+ *   - "f16 planes" = an fp16 tensor stored as `terms` stacked planes
+ *     [terms][...]: plane 0 holds hi = fp16(x), plane 1 (terms==2) holds
+ *     lo = fp16(x - hi).  terms==1 is the TF32-like fast mode, terms==2 gives
+ *     fp32-equivalent tensor-core products via the 3-product split
+ *     (hi*hi + hi*lo + lo*hi) inside t2h_tapgemm.
+ *   - activations are NHWC inside the library; NCHW only at module boundaries.
+ */
+#ifndef T2H_H_
+#define T2H_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2H_VERSION 100
+
+#define T2H_OK 0
+#define T2H_EINVAL (-1)   /* bad argument / unsupported shape            */
+#define T2H_ECUDA (-2)    /* CUDA runtime / driver error                  */
+#define T2H_EARCH (-3)    /* device is not sm_100                         */
+
+typedef void* t2h_stream_t; /* cudaStream_t */
+
+int t2h_version(void);
+const char* t2h_last_error(void);
+/* compute capability and SM count of the current device */
+int t2h_device_info(int* cc_major, int* cc_minor, int* num_sms);
+
+/* ------------------------------------------------------------------------
+ * t2h_tapgemm — tcgen05/TMEM/TMA implicit-GEMM.
+ *
+ *   D[n,h,w,:] = epilogue( sum_{tap} sum_{c} A[n, h+dy(tap), w+dx(tap), c] *
+ *                                             B[tap, :, c] )
+ *
+ * One kernel serves every dense contraction on the path:
+ *   3x3 conv s1 p1      torch.nn.Conv2d in ResnetBlock/conv_in/conv_out/Upsample
+ *                       (vqgan_arch.py:573,579,526,840,885,954,997)
+ *   3x3 conv s2 (0,1,0,1) pad   Downsample (vqgan_arch.py:544-551) — A is the
+ *                       4-phase space-to-depth view, taps carry a phase offset
+ *   1x1 conv / Linear   nin_shortcut :590, AttnBlock q/k/v/proj :627-634,
+ *                       quant_conv/post_quant_conv (vqgan_model.py:418-422),
+ *                       nn.Linear in transformer_arch.py:21-28,85-87,233
+ *   batched bmm         AttnBlock torch.bmm :648,:655; q@k^T, att@v
+ *                       (transformer_arch.py:58,65)
+ *
+ * A is an fp16-plane tensor addressed as (c, w, h, img) with element strides
+ * (1, a_sw, a_sh, a_sn); out-of-range (h,w,c) reads are zero (TMA OOB fill),
+ * which implements the conv zero padding.  B is an fp16-plane tensor addressed
+ * as (k, n, g) with strides (1, b_sn, b_sg); g = tap index (conv) or batch
+ * index (bmm).  Accumulation is fp32 in tensor memory.
+ * ---------------------------------------------------------------------- */
+#define T2H_MAX_TAPS 9
+
+#define T2H_OUT_F32 0        /* fp32 output                                  */
+#define T2H_OUT_PLANES 1     /* fp16 planes output (d_terms planes)          */
+
+#define T2H_BIAS_NONE 0
+#define T2H_BIAS_COL 1       /* bias[n_out]   (conv / Linear bias)            */
+#define T2H_BIAS_ROW 2       /* bias[h*W + w] (transposed products, V^T)      */
+
+#define T2H_ACT_NONE 0
+#define T2H_ACT_GELU 1       /* exact erf GELU, nn.GELU() transformer_arch.py:86 */
+
+typedef struct t2h_tapgemm_params {
+  /* ---- A operand (activations) ---- */
+  const void* a;         /* fp16 planes                                      */
+  int32_t a_terms;       /* 1 or 2 planes present                            */
+  int32_t a_term_imgs;   /* img-index distance between plane 0 and plane 1   */
+  int32_t a_imgs;        /* total img slots addressable in the map (all planes, phases) */
+  int32_t a_bcast;       /* 1: A has a single image shared by all n (batch-broadcast) */
+  int32_t n_img, H, W;   /* output domain: n_img images of HxW rows           */
+  int32_t a_H, a_W;      /* extents of A's (h,w) dims (OOB beyond => 0)      */
+  int32_t C;             /* contraction length per tap (valid channels)      */
+  int64_t a_sw, a_sh, a_sn; /* element strides of A                          */
+  /* ---- B operand (weights / second matrix) ---- */
+  const void* b;         /* fp16 planes, (k, n, g)                           */
+  int32_t b_terms;       /* 1 or 2                                           */
+  int32_t b_term_g;      /* g-index distance between plane 0 and plane 1     */
+  int32_t b_groups;      /* total g slots addressable                        */
+  int32_t b_batched;     /* 1: g += image index n (bmm)                      */
+  int32_t n_out;         /* valid output columns (rows of B)                 */
+  int64_t b_sn, b_sg;    /* element strides of B                             */
+  /* ---- taps ---- */
+  int32_t ntaps;
+  int32_t tap_dy[T2H_MAX_TAPS];
+  int32_t tap_dx[T2H_MAX_TAPS];
+  int32_t tap_img_off[T2H_MAX_TAPS]; /* added to A's img index (stride-2 phases) */
+  /* ---- products ---- */
+  int32_t nterms;        /* 1: hi*hi   3: hi*hi + hi*lo + lo*hi               */
+  /* ---- epilogue ---- */
+  void* d;               /* output                                           */
+  int32_t d_mode;        /* T2H_OUT_*                                        */
+  int32_t d_terms;       /* planes written when d_mode == PLANES             */
+  int64_t d_plane;       /* element distance between output planes           */
+  int64_t d_sn, d_sh, d_sw, d_sc; /* element strides of D (d_sc==1 => NHWC)   */
+  const float* bias;     /* fp32, may be NULL                                */
+  int32_t bias_mode;     /* T2H_BIAS_*                                       */
+  int32_t act;           /* T2H_ACT_*                                        */
+  float alpha;           /* acc *= alpha before bias                         */
+  const float* residual; /* fp32, same addressing as D (f32 mode), or NULL   */
+  double* gn_stats;      /* optional [n_img][32][2] (sum, sumsq) accumulators
+                            of the fp32 output, for the following GroupNorm   */
+  int32_t gn_cpg;        /* channels per group when gn_stats != NULL         */
+} t2h_tapgemm_params;
+
+int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Layout / precision conversion (HBM-bound)
+ * ---------------------------------------------------------------------- */
+/* fp32 NCHW [N,C,H,W] -> fp16 planes NHWC [terms][N][H][W][c_pad], zero
+ * channel padding.  Entry of Encoder/Decoder.forward (vqgan_arch.py:899,1008). */
+int t2h_nchw_to_planes(const float* x, void* out, int n, int c, int h, int w,
+                       int c_pad, int terms, t2h_stream_t stream);
+/* fp32 NHWC [N,H,W,C] -> fp32 NCHW.  Exit of the modules. */
+int t2h_nhwc_to_nchw(const float* x, float* out, int n, int c, int h, int w,
+                     t2h_stream_t stream);
+/* fp32 NCHW -> fp32 NHWC */
+int t2h_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w,
+                     t2h_stream_t stream);
+
+#define T2H_CVT_PLAIN 0
+#define T2H_CVT_UP2X 1   /* nearest x2: F.interpolate in Upsample (vqgan_arch.py:530) */
+#define T2H_CVT_S2D 2    /* 4-phase space-to-depth for Downsample (vqgan_arch.py:547-551):
+                            out[(p*2+q)][n][oh][ow][c] = x[n][2*oh+p][2*ow+q][c]  */
+/* fp32 NHWC [N,H,W,C] -> fp16 planes.  Output spatial size is (2H,2W) for UP2X,
+ * (H/2,W/2) x 4 phases for S2D.  Plane layout: [terms][phases][N][h][w][C]. */
+int t2h_f32_to_planes(const float* x, void* out, int n, int h, int w, int c,
+                      int mode, int terms, t2h_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * GroupNorm(32, C, eps) (+ swish)  — Normalize()/nonlinearity(),
+ * vqgan_arch.py:510-517, used at :599-600,:606-607,:638,:916-917,:1030-1031
+ * ---------------------------------------------------------------------- */
+/* stats[n][g] = (sum, sumsq) in fp64 over fp32 NHWC x.  stats must be zeroed
+ * by the caller (or produced by t2h_tapgemm's gn_stats epilogue instead). */
+int t2h_gn_stats(const float* x, double* stats, int n, int hw, int c, int groups,
+                 t2h_stream_t stream);
+/* y = gn(x)*gamma+beta, optionally * sigmoid(.)  -> fp16 planes NHWC */
+int t2h_gn_apply(const float* x, const double* stats, const float* gamma,
+                 const float* beta, void* out, int n, int hw, int c, int groups,
+                 float eps, int swish, int terms, t2h_stream_t stream);
+
+/* x += y (fp32): `h += bot_h`, vqgan_arch.py:1024 */
+int t2h_add_inplace(float* x, const float* y, int64_t numel, t2h_stream_t stream);
+
+/* softmax over the last dim of fp32 [rows, cols] * scale -> fp16 planes
+ * (F.softmax, vqgan_arch.py:649-650, transformer_arch.py:58-63) */
+int t2h_softmax_rows(const float* s, void* out, int64_t rows, int cols, float scale,
+                     int terms, t2h_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Codebook quantizers (fp32 CUDA-core math, bit-reproducible; see
+ * oracle/vq_oracle.c for the exact operation order)
+ *   VectorQuantizer.forward                  vqgan_arch.py:79-122
+ *   VectorQuantizerTexture.forward           vqgan_arch.py:212-287
+ *   VectorQuantizerSpatialTextureAware.fwd   vqgan_arch.py:375-461
+ *
+ * z:        fp32 NHWC [B, Hz, Wz, Cz]
+ * codebook: fp32 [n_books][n_e][D],  D = Cz * ps * ps  (ps = patch size 1|2);
+ *           row element order is (c, kh, kw) as F.unfold produces (:324)
+ * book_id:  int32 [B * Hz/ps * Wz/ps] codebook chosen per row (value outside
+ *           [0,n_books) => row untouched: z_q row = 0, indices = -1), or NULL
+ *           for the single-codebook quantizer
+ * idx:      int64 [rows] argmin (lowest index wins ties), -1 when unselected
+ * idx_cont: int64 [rows] idx + n_e_cont_stride*book (reference uses 1024*k for
+ *           the top quantizer :262 and n_e*k for the bottom :436), may be NULL
+ * idx_list: int64 [n_books][rows] per-codebook maps filled with -1 elsewhere
+ *           (:238-242,:257-259), may be NULL
+ * zq_nhwc:  fp32 NHWC quantized values (straight-through value z + (z_q - z),
+ *           :281), may be NULL
+ * zq_nchw:  fp32 NCHW of the same, may be NULL
+ * sqerr:    double[1] += sum (z_q - z)^2 (for the codebook loss :273-278), may be NULL
+ * ---------------------------------------------------------------------- */
+int t2h_vq_search(const float* z, const float* codebook, const int32_t* book_id,
+                  int b, int hz, int wz, int cz, int ps, int n_books, int n_e,
+                  int64_t cont_stride, int64_t* idx, int64_t* idx_cont,
+                  int64_t* idx_list, float* zq_nhwc, float* zq_nchw, double* sqerr,
+                  void* workspace, int64_t workspace_bytes, t2h_stream_t stream);
+/* bytes of workspace t2h_vq_search needs for `rows` rows */
+int64_t t2h_vq_workspace_bytes(int64_t rows, int n_books, int n_e);
+
+/* get_codebook_entry (vqgan_arch.py:124-139, :289-309, :463-486): gather rows
+ * by index -> fp32 NHWC [B, Hz, Wz, Cz] (patch-folded when ps == 2).
+ * idx: int64 [rows] per-row index inside its codebook (already resolved from
+ * indices_list by the caller), book_id as above. */
+int t2h_vq_gather(const float* codebook, const int64_t* idx, const int32_t* book_id,
+                  int b, int hz, int wz, int cz, int ps, int n_books, int n_e,
+                  float* zq_nhwc, float* zq_nchw, t2h_stream_t stream);
+
+/* nearest-neighbour resize of a float id map [B,1,Hs,Ws] to int32 [B,Ht,Wt]
+ * (F.interpolate(mode='nearest'), vqgan_arch.py:222,:385-389) */
+int t2h_mask_to_ids(const float* mask, int32_t* ids, int b, int hs, int ws, int ht,
+                    int wt, t2h_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Transformer pieces (transformer_arch.py)
+ * ---------------------------------------------------------------------- */
+/* x[b,t,:] = tok_emb[idx] + pos_emb[t] + segm_emb[segm] + tex_emb[tex]  (:251-266) fp32 */
+int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex,
+                  const float* tok_emb, const float* pos_emb, const float* segm_emb,
+                  const float* tex_emb, float* x, int b, int t, int c,
+                  t2h_stream_t stream);
+/* LayerNorm over the last dim (eps 1e-5) of fp32 [rows, c] -> fp16 planes (:80-81,:231) */
+int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* out,
+                  int64_t rows, int c, float eps, int terms, t2h_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2H_H_ */

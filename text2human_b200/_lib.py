@@ -1,0 +1,96 @@
+"""ctypes binding of libt2h.so (the C ABI declared in include/t2h.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` /
+``text2human_b200/csrc/Makefile``.  There is no CPU or PyTorch fallback: if the
+shared object is missing, loading fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt2h.so")
+
+MAX_TAPS = 9
+OUT_F32, OUT_PLANES = 0, 1
+BIAS_NONE, BIAS_COL, BIAS_ROW = 0, 1, 2
+ACT_NONE, ACT_GELU = 0, 1
+CVT_PLAIN, CVT_UP2X, CVT_S2D = 0, 1, 2
+
+
+class TapGemmParams(C.Structure):
+    """Mirror of ``t2h_tapgemm_params`` (include/t2h.h) — field order matters."""
+    _fields_ = [
+        ("a", C.c_void_p), ("a_terms", C.c_int32), ("a_term_imgs", C.c_int32),
+        ("a_imgs", C.c_int32), ("a_bcast", C.c_int32),
+        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("a_H", C.c_int32), ("a_W", C.c_int32), ("C", C.c_int32),
+        ("a_sw", C.c_int64), ("a_sh", C.c_int64), ("a_sn", C.c_int64),
+        ("b", C.c_void_p), ("b_terms", C.c_int32), ("b_term_g", C.c_int32),
+        ("b_groups", C.c_int32), ("b_batched", C.c_int32), ("n_out", C.c_int32),
+        ("b_sn", C.c_int64), ("b_sg", C.c_int64),
+        ("ntaps", C.c_int32),
+        ("tap_dy", C.c_int32 * MAX_TAPS), ("tap_dx", C.c_int32 * MAX_TAPS),
+        ("tap_img_off", C.c_int32 * MAX_TAPS),
+        ("nterms", C.c_int32),
+        ("d", C.c_void_p), ("d_mode", C.c_int32), ("d_terms", C.c_int32),
+        ("d_plane", C.c_int64),
+        ("d_sn", C.c_int64), ("d_sh", C.c_int64), ("d_sw", C.c_int64), ("d_sc", C.c_int64),
+        ("bias", C.c_void_p), ("bias_mode", C.c_int32), ("act", C.c_int32),
+        ("alpha", C.c_float),
+        ("residual", C.c_void_p),
+        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/t2h.h declares
+_I, _L, _P, _F = C.c_int, C.c_int64, C.c_void_p, C.c_float
+SIGNATURES = {
+    "t2h_version": (_I, []),
+    "t2h_last_error": (C.c_char_p, []),
+    "t2h_device_info": (_I, [C.POINTER(_I)] * 3),
+    "t2h_tapgemm": (_I, [C.POINTER(TapGemmParams), _P]),
+    "t2h_nchw_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "t2h_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "t2h_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "t2h_f32_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "t2h_gn_stats": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "t2h_gn_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
+    "t2h_add_inplace": (_I, [_P, _P, _L, _P]),
+    "t2h_softmax_rows": (_I, [_P, _P, _L, _I, _F, _I, _P]),
+    "t2h_vq_search": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P,
+                           _P, _L, _P]),
+    "t2h_vq_workspace_bytes": (_L, [_L, _I, _I]),
+    "t2h_vq_gather": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "t2h_mask_to_ids": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "t2h_embed_sum": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "t2h_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
+}
+
+_lib = None
+
+
+class T2HError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libt2h.so (once).  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise T2HError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C text2human_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise T2HError(f"libt2h error {rc}: {load().t2h_last_error().decode()}")

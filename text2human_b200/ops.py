@@ -1,0 +1,371 @@
+"""Thin torch-tensor wrappers over the libt2h C ABI.
+
+PyTorch is only plumbing here: device memory (``torch.empty``) and the current
+CUDA stream.  Every numerical operation is a libt2h kernel; a missing library
+or a non-CUDA tensor raises instead of falling back.
+
+"planes" tensors are ``torch.float16`` tensors whose leading dim is the number
+of split terms T (1 = TF32-like fast mode, 2 = hi/lo pair for fp32-equivalent
+3-product contractions); the remaining dims are the logical NHWC / matrix dims.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, BIAS_COL, BIAS_NONE, BIAS_ROW, CVT_PLAIN, CVT_S2D, CVT_UP2X,
+                   OUT_F32, OUT_PLANES, TapGemmParams)
+
+# ----------------------------------------------------------------------------
+# precision policy
+# ----------------------------------------------------------------------------
+_PRECISION = {"terms": 2}
+
+
+def set_precision(mode):
+    """"fp32" : hi/lo fp16 planes, 3 tensor-core products per contraction
+    (fp32-equivalent; the parity mode).  "fp16": single fp16 plane, one product
+    (10-bit mantissa operands like TF32, fp32 accumulate; the fast mode)."""
+    if mode in ("fp32", "fp16x3", "exact"):
+        _PRECISION["terms"] = 2
+    elif mode in ("fp16", "fast", "tf32"):
+        _PRECISION["terms"] = 1
+    else:
+        raise ValueError(f"unknown precision mode {mode!r}")
+
+
+def get_terms():
+    return _PRECISION["terms"]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.T2HError("text2human_b200 kernels need CUDA tensors; there is no CPU path")
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+# ----------------------------------------------------------------------------
+# the tensor-core contraction
+# ----------------------------------------------------------------------------
+_TAPS_1 = ((0, 0, 0),)
+_TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
+
+
+def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
+             b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
+             d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None):
+    lib = _lib.load()
+    T = a.shape[0]
+    Tb = b.shape[0]
+    p = TapGemmParams()
+    p.a = a.data_ptr(); p.a_terms = T; p.a_term_imgs = a_term_imgs; p.a_imgs = a_imgs
+    p.a_bcast = a_bcast
+    p.n_img, p.H, p.W, p.a_H, p.a_W, p.C = n_img, H, W, a_H, a_W, Cc
+    p.a_sw, p.a_sh, p.a_sn = a_sw, a_sh, a_sn
+    p.b = b.data_ptr(); p.b_terms = Tb; p.b_term_g = b_term_g; p.b_groups = b_groups
+    p.b_batched = b_batched; p.n_out = n_out; p.b_sn = b_sn; p.b_sg = b_sg
+    p.ntaps = len(taps)
+    for i, (dy, dx, off) in enumerate(taps):
+        p.tap_dy[i], p.tap_dx[i], p.tap_img_off[i] = dy, dx, off
+    p.nterms = 3 if (T == 2 and Tb == 2) else 1
+    p.d = d.data_ptr(); p.d_mode = d_mode
+    p.d_terms = d.shape[0] if d_mode == OUT_PLANES else 0
+    p.d_plane = d_plane
+    p.d_sn, p.d_sh, p.d_sw, p.d_sc = d_strides
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.bias_mode = bias_mode if bias is not None else BIAS_NONE
+    p.act = act
+    p.alpha = alpha
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.gn_stats = None
+    p.gn_cpg = 0
+    _lib.check(lib.t2h_tapgemm(C.byref(p), _stream()))
+
+
+def _alloc_out(shape, planes, terms, device):
+    if planes:
+        return torch.empty((terms,) + tuple(shape), dtype=torch.float16, device=device)
+    return torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
+def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False):
+    """3x3 stride-1 pad-1 conv.  a: planes [T,N,H,W,C]; w: packed planes
+    [T,9,Cout,C] (see pack_conv_weight); bias fp32 [Cout].  Returns fp32 NHWC
+    [N,H,W,Cout] (or NCHW with nchw_out) or planes [T,N,H,W,Cout]."""
+    _need_cuda(a, w)
+    T, N, H, W, Cc = a.shape
+    Cout = w.shape[2]
+    assert w.shape[1] == 9 and w.shape[3] == Cc, (a.shape, w.shape)
+    if nchw_out:
+        out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=a.device)
+        d_strides = (Cout * H * W, W, 1, H * W)
+    else:
+        out = _alloc_out((N, H, W, Cout), planes_out, T, a.device)
+        d_strides = (H * W * Cout, W * Cout, Cout, 1)
+    _tapgemm(a=a, a_term_imgs=N, a_imgs=T * N, a_bcast=0, n_img=N, H=H, W=W, a_H=H, a_W=W, Cc=Cc,
+             a_sw=Cc, a_sh=W * Cc, a_sn=H * W * Cc,
+             b=w, b_term_g=9, b_groups=w.shape[0] * 9, b_batched=0, n_out=Cout, b_sn=Cc, b_sg=Cout * Cc,
+             taps=_TAPS_3x3, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
+             d_plane=N * H * W * Cout, bias=bias, bias_mode=BIAS_COL, residual=residual)
+    return out
+
+
+def conv3x3_s2(a_ph, w, bias):
+    """Downsample conv: pad (0,1,0,1) then 3x3 stride 2 (vqgan_arch.py:547-551).
+    a_ph: space-to-depth planes [T,4,N,Ho,Wo,C] from f32_to_planes(mode=S2D)."""
+    _need_cuda(a_ph, w)
+    T, four, N, Ho, Wo, Cc = a_ph.shape
+    assert four == 4
+    Cout = w.shape[2]
+    out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=a_ph.device)
+    taps = tuple((kh // 2, kw // 2, ((kh % 2) * 2 + (kw % 2)) * N) for kh in range(3) for kw in range(3))
+    _tapgemm(a=a_ph, a_term_imgs=4 * N, a_imgs=T * 4 * N, a_bcast=0, n_img=N, H=Ho, W=Wo, a_H=Ho, a_W=Wo,
+             Cc=Cc, a_sw=Cc, a_sh=Wo * Cc, a_sn=Ho * Wo * Cc,
+             b=w, b_term_g=9, b_groups=w.shape[0] * 9, b_batched=0, n_out=Cout, b_sn=Cc, b_sg=Cout * Cc,
+             taps=taps, d=out, d_mode=OUT_F32, d_strides=(Ho * Wo * Cout, Wo * Cout, Cout, 1),
+             bias=bias, bias_mode=BIAS_COL)
+    return out
+
+
+def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None):
+    """a: planes [T,M,K] (any leading dims are flattened by the caller);
+    w: planes [T,1,Nout,K] (pack_linear_weight).  -> fp32 [M,Nout] or planes [T,M,Nout].
+    Serves 1x1 convs on NHWC activations and nn.Linear."""
+    _need_cuda(a, w)
+    T, M, K = a.shape
+    Nout = w.shape[2]
+    assert w.shape[3] == K and a.stride(2) == 1, (a.shape, w.shape)
+    if out is None:
+        out = _alloc_out((M, Nout), planes_out, T, a.device)
+    a_sw = a.stride(1)
+    _tapgemm(a=a, a_term_imgs=1, a_imgs=T, a_bcast=0, n_img=1, H=1, W=M, a_H=1, a_W=M, Cc=K,
+             a_sw=a_sw, a_sh=a.stride(0), a_sn=a.stride(0),
+             b=w, b_term_g=1, b_groups=w.shape[0], b_batched=0, n_out=Nout, b_sn=w.stride(2),
+             b_sg=w.stride(0),
+             taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
+             d_strides=(0, 0, out.stride(-2), 1), d_plane=out.stride(0) if planes_out else 0,
+             bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual)
+    return out
+
+
+def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False):
+    """out[g] = a[g] @ b[g]^T.  a: planes [T,G,M,K] (or [T,1,M,K] with a_bcast);
+    b: planes [T,G,N,K]; views with a unit last stride are accepted.
+    -> fp32 [G,M,N] or planes [T,G,M,N]."""
+    _need_cuda(a, b)
+    T, Ga, M, K = a.shape
+    Tb, G, N, Kb = b.shape
+    assert K == Kb and a.stride(3) == 1 and b.stride(3) == 1
+    assert (Ga == G) or (a_bcast and Ga == 1)
+    out = _alloc_out((G, M, N), planes_out, T, a.device)
+    a_sn = a.stride(1)
+    b_sg = b.stride(1)
+    a_term_imgs = 1 if T == 1 else a.stride(0) // a_sn
+    b_term_g = 1 if Tb == 1 else b.stride(0) // b_sg
+    assert T == 1 or a.stride(0) % a_sn == 0
+    assert Tb == 1 or b.stride(0) % b_sg == 0
+    _tapgemm(a=a, a_term_imgs=a_term_imgs, a_imgs=(T - 1) * a_term_imgs + Ga, a_bcast=1 if a_bcast else 0,
+             n_img=G, H=1, W=M, a_H=1, a_W=M, Cc=K, a_sw=a.stride(2), a_sh=a_sn, a_sn=a_sn,
+             b=b, b_term_g=b_term_g, b_groups=(Tb - 1) * b_term_g + G, b_batched=1, n_out=N,
+             b_sn=b.stride(2), b_sg=b_sg,
+             taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
+             d_strides=(M * N, 0, N, 1), d_plane=G * M * N,
+             bias=bias_row, bias_mode=BIAS_ROW, alpha=alpha)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# weight packing (one-time host-side preparation, cached by the modules)
+# ----------------------------------------------------------------------------
+def split_planes(x, terms):
+    """fp32 tensor -> fp16 planes [terms, ...] (hi, lo)."""
+    x = x.detach().float()
+    hi = x.half()
+    if terms == 1:
+        return hi.unsqueeze(0).contiguous()
+    lo = (x - hi.float()).half()
+    return torch.stack((hi, lo)).contiguous()
+
+
+def pack_conv_weight(w, terms, c_pad=None):
+    """OIHW fp32 conv weight -> planes [T, kh*kw, Cout, Cin_pad] (tap-major, K-contiguous)."""
+    Cout, Cin, kh, kw = w.shape
+    wt = w.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin)
+    cp = c_pad if c_pad is not None else (Cin + 7) // 8 * 8
+    if cp != Cin:
+        wt = torch.nn.functional.pad(wt, (0, cp - Cin))
+    return split_planes(wt, terms)
+
+
+def pack_linear_weight(w, terms):
+    """[out, in] fp32 (nn.Linear / 1x1 conv weight squeezed) -> planes [T,1,out,in]."""
+    w2 = w.detach().float().reshape(w.shape[0], -1)
+    return split_planes(w2.unsqueeze(0), terms)
+
+
+# ----------------------------------------------------------------------------
+# HBM-bound kernels
+# ----------------------------------------------------------------------------
+def nchw_to_planes(x, c_pad=None, terms=None):
+    _need_cuda(x)
+    x = _f32c(x)
+    N, Cc, H, W = x.shape
+    terms = terms or get_terms()
+    cp = c_pad if c_pad is not None else (Cc + 7) // 8 * 8
+    out = torch.empty((terms, N, H, W, cp), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.load().t2h_nchw_to_planes(_ptr(x), _ptr(out), N, Cc, H, W, cp, terms, _stream()))
+    return out
+
+
+def nhwc_to_nchw(x):
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().t2h_nhwc_to_nchw(_ptr(x), _ptr(out), N, Cc, H, W, _stream()))
+    return out
+
+
+def nchw_to_nhwc(x):
+    _need_cuda(x)
+    x = _f32c(x)
+    N, Cc, H, W = x.shape
+    out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().t2h_nchw_to_nhwc(_ptr(x), _ptr(out), N, Cc, H, W, _stream()))
+    return out
+
+
+def f32_to_planes(x, mode=CVT_PLAIN, terms=None):
+    """fp32 NHWC [N,H,W,C] -> planes.  PLAIN: [T,N,H,W,C]; UP2X: [T,N,2H,2W,C];
+    S2D: [T,4,N,H/2,W/2,C]."""
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    terms = terms or get_terms()
+    if mode == CVT_UP2X:
+        shape = (terms, N, 2 * H, 2 * W, Cc)
+    elif mode == CVT_S2D:
+        shape = (terms, 4, N, H // 2, W // 2, Cc)
+    else:
+        shape = (terms, N, H, W, Cc)
+    out = torch.empty(shape, dtype=torch.float16, device=x.device)
+    _lib.check(_lib.load().t2h_f32_to_planes(_ptr(x), _ptr(out), N, H, W, Cc, mode, terms, _stream()))
+    return out
+
+
+def group_norm(x, gamma, beta, *, swish, groups=32, eps=1e-6, terms=None):
+    """GroupNorm(32, C, eps=1e-6) (+ swish) of fp32 NHWC x -> planes [T,N,H,W,C]."""
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    terms = terms or get_terms()
+    lib = _lib.load()
+    stats = torch.zeros((N, groups, 2), dtype=torch.float64, device=x.device)
+    _lib.check(lib.t2h_gn_stats(_ptr(x), _ptr(stats), N, H * W, Cc, groups, _stream()))
+    out = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device)
+    _lib.check(lib.t2h_gn_apply(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), N, H * W, Cc,
+                                groups, eps, 1 if swish else 0, terms, _stream()))
+    return out
+
+
+def add_inplace(x, y):
+    _need_cuda(x, y)
+    assert x.shape == y.shape and x.is_contiguous() and y.is_contiguous()
+    _lib.check(_lib.load().t2h_add_inplace(_ptr(x), _ptr(y), x.numel(), _stream()))
+    return x
+
+
+def softmax_rows(s, scale=1.0, terms=None):
+    """softmax(s * scale) over the last dim of fp32 s -> planes [T, *s.shape]."""
+    _need_cuda(s)
+    terms = terms or get_terms()
+    cols = s.shape[-1]
+    rows = s.numel() // cols
+    out = torch.empty((terms,) + tuple(s.shape), dtype=torch.float16, device=s.device)
+    _lib.check(_lib.load().t2h_softmax_rows(_ptr(s), _ptr(out), rows, cols, scale, terms, _stream()))
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, terms=None):
+    """LayerNorm over the last dim of fp32 [rows, C] -> planes [T, rows, C]."""
+    _need_cuda(x)
+    terms = terms or get_terms()
+    rows, Cc = x.shape
+    out = torch.empty((terms, rows, Cc), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.load().t2h_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, Cc, eps, terms,
+                                         _stream()))
+    return out
+
+
+def embed_sum(idx, segm, tex, tok_emb, pos_emb, segm_emb, tex_emb):
+    _need_cuda(idx, tok_emb)
+    B, T = idx.shape
+    Cc = tok_emb.shape[1]
+    x = torch.empty((B * T, Cc), dtype=torch.float32, device=idx.device)
+    _lib.check(_lib.load().t2h_embed_sum(_ptr(idx.contiguous()), _ptr(segm.contiguous()),
+                                         _ptr(tex.contiguous()), _ptr(tok_emb), _ptr(pos_emb),
+                                         _ptr(segm_emb), _ptr(tex_emb), _ptr(x), B, T, Cc, _stream()))
+    return x
+
+
+def mask_to_ids(mask, ht, wt):
+    """float id map [B,1,Hs,Ws] -> int32 [B,ht,wt] (nearest)."""
+    _need_cuda(mask)
+    mask = _f32c(mask)
+    B, _, Hs, Ws = mask.shape
+    ids = torch.empty((B, ht, wt), dtype=torch.int32, device=mask.device)
+    _lib.check(_lib.load().t2h_mask_to_ids(_ptr(mask), _ptr(ids), B, Hs, Ws, ht, wt, _stream()))
+    return ids
+
+
+# ----------------------------------------------------------------------------
+# quantizers
+# ----------------------------------------------------------------------------
+def vq_search(z_nhwc, codebook, book_id, *, ps=1, cont_stride=None, want_list=True, want_nchw=True,
+              want_nhwc=True, want_err=True):
+    """z_nhwc fp32 [B,Hz,Wz,Cz]; codebook fp32 [n_books,n_e,D]; book_id int32 [B,Hp,Wp] or None.
+    Returns dict(idx, idx_cont, idx_list, zq_nhwc, zq_nchw, sqerr)."""
+    _need_cuda(z_nhwc, codebook)
+    lib = _lib.load()
+    B, Hz, Wz, Cz = z_nhwc.shape
+    n_books, n_e, D = codebook.shape
+    assert D == Cz * ps * ps
+    Hp, Wp = Hz // ps, Wz // ps
+    rows = B * Hp * Wp
+    dev = z_nhwc.device
+    idx = torch.empty((B, Hp, Wp), dtype=torch.int64, device=dev)
+    idx_cont = torch.empty((B, Hp, Wp), dtype=torch.int64, device=dev)
+    idx_list = torch.empty((n_books, B, Hp, Wp), dtype=torch.int64, device=dev) if want_list else None
+    zq_nhwc = torch.empty_like(z_nhwc) if want_nhwc else None
+    zq_nchw = torch.empty((B, Cz, Hz, Wz), dtype=torch.float32, device=dev) if want_nchw else None
+    sqerr = torch.zeros((1,), dtype=torch.float64, device=dev) if want_err else None
+    wsb = lib.t2h_vq_workspace_bytes(rows, n_books, n_e)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    _lib.check(lib.t2h_vq_search(_ptr(z_nhwc), _ptr(codebook), _ptr(book_id), B, Hz, Wz, Cz, ps, n_books,
+                                 n_e, n_e if cont_stride is None else cont_stride, _ptr(idx),
+                                 _ptr(idx_cont), _ptr(idx_list), _ptr(zq_nhwc), _ptr(zq_nchw), _ptr(sqerr),
+                                 _ptr(ws), wsb, _stream()))
+    return dict(idx=idx, idx_cont=idx_cont, idx_list=idx_list, zq_nhwc=zq_nhwc, zq_nchw=zq_nchw,
+                sqerr=sqerr)
+
+
+def vq_gather(codebook, idx, book_id, *, B, Hz, Wz, Cz, ps=1, want_nchw=True, want_nhwc=False):
+    _need_cuda(codebook, idx)
+    n_books, n_e, D = codebook.shape
+    dev = codebook.device
+    zq_nhwc = torch.empty((B, Hz, Wz, Cz), dtype=torch.float32, device=dev) if want_nhwc else None
+    zq_nchw = torch.empty((B, Cz, Hz, Wz), dtype=torch.float32, device=dev) if want_nchw else None
+    _lib.check(_lib.load().t2h_vq_gather(_ptr(codebook), _ptr(idx.contiguous()), _ptr(book_id), B, Hz, Wz,
+                                         Cz, ps, n_books, n_e, _ptr(zq_nhwc), _ptr(zq_nchw), _stream()))
+    return zq_nhwc, zq_nchw
