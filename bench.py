@@ -1,0 +1,312 @@
+"""bench.py — headline benchmark of the Text2Human VQ hot path on B200.
+
+Metric (BASELINE.json): 512x256 images/s, vqvae_top encode -> quantize -> decode.
+Workload (configs[1]): vqvae_top.yml nets, batch 16 x 3x512x256 per GPU, codebook 18x1024x256,
+synthetic images/masks, random-init weights.  One "step" = one forward_step over one batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU); the path shards over independent images (replicas,
+weak scaling), there is no data-path collective — only the timing reduction (max over ranks).
+`--impl reference` times the CPU port of the reference path (oracle/vqgan_ref.py) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+VQVAE_TOP = dict(embed_dim=256, n_embed=1024, double_z=False, z_channels=256, resolution=512, in_channels=3,
+                 out_ch=3, ch=128, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2, attn_resolutions=[32],
+                 dropout=0.0)
+GFLOP_PER_IMG = 784.4  # reference op graph, 2*MAC (SURVEY.md §8a / BASELINE.md §3)
+METRIC = "512x256 images/sec VQ enc-quant-dec (vqvae_top)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_inputs(batch, n_variants, seed):
+    import golden_recipes as R
+    xs, ms = [], []
+    for i in range(n_variants):
+        xs.append(R.image(seed + i, batch, 3, 512, 256))
+        ms.append(R.blocky_mask(seed + i, batch, 512, 256, 32))
+    return xs, ms
+
+
+def cpu_port_rate(threads, runs, batch=1):
+    """images/s of the reference path restated in fp32 PyTorch on the host cores (oracle port)"""
+    from oracle import vqgan_ref
+    import golden_recipes as R
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+    torch.set_num_threads(threads)
+    torch.manual_seed(2021)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        m = VQImageSegmTextureModel(VQVAE_TOP).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cb = torch.stack([e.weight.detach() for e in m.quantize.embedding_list])
+    x = R.image(2021, batch, 3, 512, 256)
+    mask = R.blocky_mask(2021, batch, 512, 256, 32)
+    times = []
+    with torch.no_grad():
+        vqgan_ref.vq_forward_step(sd, cb, x, mask)  # warm-up
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            vqgan_ref.vq_forward_step(sd, cb, x, mask)
+            times.append(time.perf_counter() - t0)
+    return batch / min(times), batch / (sum(times) / len(times)), times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path (PyTorch fp32, oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t_all = []
+    from oracle import vqgan_ref
+    import golden_recipes as R
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+    torch.set_num_threads(threads)
+    torch.manual_seed(2021)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        m = VQImageSegmTextureModel(VQVAE_TOP).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cb = torch.stack([e.weight.detach() for e in m.quantize.embedding_list])
+    x = R.image(2021, 1, 3, 512, 256)
+    mask = R.blocky_mask(2021, 1, 512, 256, 32)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            vqgan_ref.vq_forward_step(sd, cb, x, mask)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            vqgan_ref.vq_forward_step(sd, cb, x, mask)
+        total = time.perf_counter() - t0
+    value = args.steps / total
+    line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="vqvae_top.yml enc-quant-dec 512x256, CPU port of the reference path",
+                            step="1 image (bounded sample of the batch-16 workload)"),
+                cpu_baseline=dict(value=value, unit="img/s", cores=threads, kind="port",
+                                  sample=f"{args.steps} steps x 1 image 512x256, torch fp32, {threads} threads"),
+                e2e=dict(value=value, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from text2human_b200 import _lib, ops
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    ops.set_precision(args.precision)
+
+    torch.manual_seed(2021)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the Decoder constructor prints its z-shape like the reference
+        model = VQImageSegmTextureModel(VQVAE_TOP).to(dev).eval()
+    B = args.batch
+    n_var = 3
+    xs_h, ms_h = make_inputs(B, n_var, 100 + rank * 10)
+    xs_h = [x.pin_memory() for x in xs_h]
+    ms_h = [m.pin_memory() for m in ms_h]
+    xs_d = [x.to(dev) for x in xs_h]
+    ms_d = [m.to(dev) for m in ms_h]
+    out_h = torch.empty((B, 3, 512, 256), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(args.warmup):
+        model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.COUNTERS["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dec, loss = model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    launches = ops.COUNTERS["launches"] - l0
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    def e2e_step(i):
+        x = xs_h[i % n_var].to(dev, non_blocking=True)
+        m = ms_h[i % n_var].to(dev, non_blocking=True)
+        dec, loss = model.forward_step(x, m)
+        out_h.copy_(dec, non_blocking=True)
+        return loss
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = xs_h[0].numel() * 4 + ms_h[0].numel() * 4
+    d2h = out_h.numel() * 4
+
+    # ---------------- roofline of the dominant kernel (t2h tapgemm), instrumented pass ----------------
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        ops.profile_tapgemm(True)
+        model.forward_step(xs_d[0], ms_d[0])
+        torch.cuda.synchronize()
+        rec = ops.profile_records()
+        algo = sum(r[0] for r in rec)
+        issued = sum(r[1] for r in rec)
+        t_ms = sum(r[2].elapsed_time(r[3]) for r in rec)
+        ops.profile_tapgemm(False)
+        achieved = algo / (t_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="t2h::tapgemm_kernel (tcgen05 implicit GEMM)", achieved=achieved,
+                    peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"],
+                    traffic=None, peak_source=pk["source"] + ", bf16 sustained",
+                    launches_per_step=len(rec), kernel_ms_per_step=t_ms,
+                    kernel_share_of_step=t_ms / (ms_total / args.steps),
+                    algorithmic_tflop_per_step=algo / 1e12,
+                    issued_tensor_tflops=issued / (t_ms * 1e-3) / 1e12,
+                    issued_frac=issued / (t_ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                    note="algorithmic FLOPs = 2*MAC of the reference op graph; in fp32 mode each product is "
+                         "issued as 3 fp16 tensor-core products (hi*hi+hi*lo+lo*hi), see issued_*")
+
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            best, mean, times = cpu_port_rate(threads, runs=3)
+            cpu = dict(value=best, unit="img/s", cores=threads, kind="port",
+                       sample=f"best of 3 runs of 1 image 512x256 (mean {mean:.3f} img/s), torch fp32 oracle "
+                              f"port of the reference path, {threads} threads")
+        line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32 (fp16x3 split products, fp32 accumulate)" if args.precision == "fp32"
+                    else "f16 operands (TF32-like), fp32 accumulate",
+                    data="synthetic",
+                    config=dict(workload="vqvae_top.yml batch=16 512x256 encode-quantize-decode, codebook 18x1024x256",
+                                batch_per_gpu=B, precision=args.precision, parallelism=f"replicas x{world}",
+                                l2="activation working set (>2 GB/step) exceeds the 126 MB L2; inputs rotate "
+                                   "over 3 distinct batches"),
+                    clocks=clk,
+                    e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
+                    pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,8 +64,11 @@ int t2h_device_info(int* cc_major, int* cc_minor, int* num_sms);
  * A is an fp16-plane tensor addressed as (c, w, h, img) with element strides
  * (1, a_sw, a_sh, a_sn); out-of-range (h,w,c) reads are zero (TMA OOB fill),
  * which implements the conv zero padding.  B is an fp16-plane tensor addressed
- * as (k, n, g) with strides (1, b_sn, b_sg); g = tap index (conv) or batch
- * index (bmm).  Accumulation is fp32 in tensor memory.
+ * as (k, n, g, g2) with strides (1, b_sn, b_sg, b_sg2); g = tap index (conv),
+ * plane index and, for two-level batches, the h index; g2 = image index (bmm).
+ * With tile_rows the (h, img) dims of A and D act as two batch dims of a plain
+ * row-major GEMM (multi-head attention: h = batch, img = head).
+ * Accumulation is fp32 in tensor memory.
  * ---------------------------------------------------------------------- */
 #define T2H_MAX_TAPS 9
 
@@ -87,6 +90,8 @@ typedef struct t2h_tapgemm_params {
   int32_t a_imgs;        /* total img slots addressable in the map (all planes, phases) */
   int32_t a_bcast;       /* 1: A has a single image shared by all n (batch-broadcast) */
   int32_t n_img, H, W;   /* output domain: n_img images of HxW rows           */
+  int32_t tile_rows;     /* 1: tiles are 128 consecutive w of one (h,img) (GEMM rows);
+                            0: auto (rows when H==1, else 2-D spatial boxes)   */
   int32_t a_H, a_W;      /* extents of A's (h,w) dims (OOB beyond => 0)      */
   int32_t C;             /* contraction length per tap (valid channels)      */
   int64_t a_sw, a_sh, a_sn; /* element strides of A                          */
@@ -94,10 +99,12 @@ typedef struct t2h_tapgemm_params {
   const void* b;         /* fp16 planes, (k, n, g)                           */
   int32_t b_terms;       /* 1 or 2                                           */
   int32_t b_term_g;      /* g-index distance between plane 0 and plane 1     */
-  int32_t b_groups;      /* total g slots addressable                        */
-  int32_t b_batched;     /* 1: g += image index n (bmm)                      */
+  int32_t b_groups;      /* total g slots addressable (taps/planes/h-batches) */
+  int32_t b_groups2;     /* extent of the second group dim g2 (>= 1)          */
+  int32_t b_batched;     /* 1: g2 = image index n (bmm over images)           */
+  int32_t b_batched_h;   /* 1: g += h (row-tile mode: h is a second batch dim) */
   int32_t n_out;         /* valid output columns (rows of B)                 */
-  int64_t b_sn, b_sg;    /* element strides of B                             */
+  int64_t b_sn, b_sg, b_sg2; /* element strides of B                         */
   /* ---- taps ---- */
   int32_t ntaps;
   int32_t tap_dy[T2H_MAX_TAPS];

@@ -1,0 +1,91 @@
+"""Deterministic recipes for weights and inputs shared by oracle/make_golden.py
+(which runs the real reference on them) and the tests (which re-create the same
+tensors without the reference).  All randomness is torch CPU generators seeded
+from (seed, crc32(name)), so values do not depend on module construction order.
+"""
+import zlib
+
+import torch
+
+
+def _gen(seed, name):
+    g = torch.Generator()
+    g.manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2**63 - 1))
+    return g
+
+
+def fill_state_dict(spec, seed):
+    """spec: iterable of (key, shape).  conv/linear/embedding weights ~ N(0, 1/fan_in) (embeddings N(0,1)*0.5),
+    biases ~ 0.1*N(0,1), norm weights 1 + 0.1*N(0,1), pos_emb/start_tok 0.02*N(0,1)."""
+    sd = {}
+    for key, shape in spec:
+        shape = tuple(shape)
+        g = _gen(seed, key)
+        r = torch.randn(shape, generator=g)
+        leaf = key.split(".")[-1]
+        parent = key.split(".")[-2] if "." in key else ""
+        if key in ("pos_emb", "start_tok"):
+            v = 0.02 * r
+        elif "emb" in parent or "embedding" in parent:
+            v = 0.5 * r
+        elif leaf == "weight" and len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            v = r / fan_in ** 0.5
+        elif leaf == "weight":  # norm scale
+            v = 1.0 + 0.1 * r
+        else:
+            v = 0.1 * r
+        sd[key] = v.float()
+    return sd
+
+
+def spec_of(module):
+    return [(k, tuple(v.shape)) for k, v in module.state_dict().items()]
+
+
+def image(seed, b, c, h, w):
+    return torch.rand((b, c, h, w), generator=_gen(seed, "image")) * 2 - 1
+
+
+def latent(seed, shape, scale=1.0, name="latent"):
+    return torch.randn(shape, generator=_gen(seed, name)) * scale
+
+
+def blocky_mask(seed, b, h, w, tile, n_ids=18, extra_ids=()):
+    """float id map [b,1,h,w], constant on tile x tile blocks; ids uniform in [0,n_ids) plus optional
+    out-of-range ids (which select no codebook)."""
+    g = _gen(seed, "mask")
+    pool = list(range(n_ids)) + list(extra_ids)
+    pick = torch.randint(0, len(pool), (b, (h + tile - 1) // tile, (w + tile - 1) // tile), generator=g)
+    ids = torch.tensor(pool, dtype=torch.float32)[pick]
+    m = ids.repeat_interleave(tile, 1).repeat_interleave(tile, 2)[:, :h, :w]
+    return m.unsqueeze(1).contiguous()
+
+
+def iid_mask(seed, b, h, w, n_ids=18):
+    g = _gen(seed, "iid_mask")
+    return torch.randint(0, n_ids, (b, 1, h, w), generator=g).float()
+
+
+def codebooks(seed, n_books, n_e, d, kind):
+    """kind 'default': the reference init uniform(-1/n_e, 1/n_e) (vqgan_arch.py:169);
+    kind 'trained': rows ~ N(0, 1) (spread like encoder outputs, so distances are not near-ties)."""
+    g = _gen(seed, "codebooks_" + kind)
+    if kind == "default":
+        return (torch.rand((n_books, n_e, d), generator=g) * 2 - 1) / n_e
+    return torch.randn((n_books, n_e, d), generator=g)
+
+
+# ---------------------------------------------------------------- model configs
+TINY_ENC = dict(ch=64, num_res_blocks=1, attn_resolutions=[8], in_channels=3, resolution=32, z_channels=32,
+                ch_mult=[1, 2, 2], double_z=False, dropout=0.0)          # x [B,3,32,16] -> z [B,32,8,4]
+TINY_DEC = dict(in_channels=3, resolution=64, z_channels=32, ch=32, out_ch=3, num_res_blocks=1,
+                attn_resolutions=[4], ch_mult=[1, 1, 1, 2, 2], dropout=0.0, resamp_with_conv=True,
+                give_pre_end=False)                                       # z [B,32,4,2] -> [B,3,64,32]
+TINY_DECRES = dict(in_channels=3, resolution=32, z_channels=32, ch=32, num_res_blocks=1, ch_mult=[1, 2, 2],
+                   dropout=0.0, give_pre_end=False)                       # z [B,32,8,4] -> [B,64,8,4]
+TINY_TRANSFORMER = dict(codebook_size=18 * 16, segm_codebook_size=32, texture_codebook_size=18, bert_n_emb=64,
+                        bert_n_layers=2, bert_n_head=4, block_size=32, latent_shape=[8, 4], embd_pdrop=0.0,
+                        resid_pdrop=0.0, attn_pdrop=0.0, num_head=18)

@@ -1,0 +1,88 @@
+"""CPU checks of the host-side logic: fp16 plane splitting, weight packing, packed-weight cache
+invalidation, state_dict (checkpoint ABI) parity with the reference key names."""
+import numpy as np
+import torch
+
+import golden_recipes as R
+from text2human_b200 import ops
+from text2human_b200 import transformer_arch as T
+from text2human_b200 import vqgan_arch as A
+
+
+def test_split_planes_reconstructs_fp32_to_22_bits():
+    x = torch.randn(1000) * 3
+    p = ops.split_planes(x, 2)
+    assert p.shape == (2, 1000) and p.dtype == torch.float16
+    # hi carries 11 bits, lo the next 11 (until lo hits the fp16 subnormal step 2^-24)
+    err = (p.float().sum(0) - x).abs()
+    assert (err <= x.abs() * 2 ** -21 + 2 ** -24).all()
+    assert torch.equal(ops.split_planes(x, 1)[0], x.half())
+
+
+def test_pack_conv_weight_layout_and_padding():
+    w = torch.randn(5, 3, 3, 3)
+    p = ops.pack_conv_weight(w, 2)
+    assert p.shape == (2, 9, 5, 8)
+    rec = p.float().sum(0)
+    for kh in range(3):
+        for kw in range(3):
+            assert torch.allclose(rec[kh * 3 + kw, :, :3], w[:, :, kh, kw], atol=1e-6)
+    assert (rec[..., 3:] == 0).all()
+    l = ops.pack_linear_weight(torch.randn(7, 16, 1, 1), 1)
+    assert l.shape == (1, 1, 7, 16)
+
+
+def test_packed_weight_cache_tracks_in_place_updates():
+    conv = torch.nn.Conv2d(8, 8, 3)
+    a = A._conv_w(conv)
+    assert A._conv_w(conv) is a
+    with torch.no_grad():
+        conv.weight.add_(1.0)
+    b = A._conv_w(conv)
+    assert b is not a
+    assert not torch.equal(a, b)
+
+
+def test_state_dict_keys_follow_reference_checkpoint_abi():
+    enc = A.Encoder(ch=128, num_res_blocks=2, attn_resolutions=[32], in_channels=3, resolution=512,
+                    z_channels=256, ch_mult=[1, 1, 2, 2, 4], double_z=False)
+    keys = list(enc.state_dict())
+    assert len(keys) == 144
+    assert sum(p.numel() for p in enc.parameters()) == 29298176
+    for k in ("conv_in.weight", "down.0.block.0.norm1.weight", "down.4.attn.1.proj_out.bias",
+              "down.3.downsample.conv.weight", "mid.attn_1.q.weight", "norm_out.bias", "conv_out.weight",
+              "down.2.block.0.nin_shortcut.weight"):
+        assert k in keys, k
+    dec = A.Decoder(in_channels=3, resolution=512, z_channels=256, ch=128, out_ch=3, num_res_blocks=2,
+                    attn_resolutions=[32], ch_mult=[1, 1, 2, 2, 4])
+    assert sum(p.numel() for p in dec.parameters()) == 42450307 or abs(
+        sum(p.numel() for p in dec.parameters()) / 1e6 - 42.45) < 0.01
+    assert "up.4.attn.2.k.weight" in dec.state_dict() and "up.1.upsample.conv.bias" in dec.state_dict()
+    q = A.VectorQuantizerTexture(1024, 256, 0.25)
+    assert list(q.state_dict())[0] == "embedding_list.0.weight" and len(q.state_dict()) == 18
+    qb = A.VectorQuantizerSpatialTextureAware(512, 256, 0.25, spatial_size=2)
+    assert qb.state_dict()["embedding_list.17.weight"].shape == (512, 1024)
+    tf = T.TransformerMultiHead(codebook_size=18432, segm_codebook_size=1024, texture_codebook_size=18,
+                                bert_n_emb=512, bert_n_layers=2, bert_n_head=8, block_size=512,
+                                latent_shape=[32, 16], embd_pdrop=0, resid_pdrop=0, attn_pdrop=0, num_head=18)
+    sd = tf.state_dict()
+    assert sd["tok_emb.weight"].shape == (18433, 512) and sd["pos_emb"].shape == (1, 512, 512)
+    assert sd["head_list.17.weight"].shape == (1024, 512)
+    for k in ("blocks.0.attn.key.weight", "blocks.1.mlp.2.bias", "ln_f.weight", "start_tok",
+              "segm_emb.weight", "texture_emb.weight"):
+        assert k in sd
+    assert (sd["pos_emb"] == 0).all() and (sd["start_tok"] == 0).all()  # reference never applies _init_weights
+
+
+def test_default_codebook_init_matches_reference_range():
+    q = A.VectorQuantizerTexture(1024, 256, 0.25)
+    w = q.embedding_list[3].weight
+    assert w.abs().max() <= 1.0 / 1024 and w.abs().max() > 0.9 / 1024
+
+
+def test_recipe_is_deterministic():
+    a = R.fill_state_dict([("x.weight", (4, 3, 3, 3)), ("x.bias", (4,))], 5)
+    b = R.fill_state_dict([("x.bias", (4,)), ("x.weight", (4, 3, 3, 3))], 5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    m = R.blocky_mask(1, 2, 64, 32, 16, extra_ids=(20,))
+    assert m.shape == (2, 1, 64, 32) and set(np.unique(m.numpy())).issubset(set(range(18)) | {20})

@@ -22,12 +22,13 @@ class TapGemmParams(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("a_terms", C.c_int32), ("a_term_imgs", C.c_int32),
         ("a_imgs", C.c_int32), ("a_bcast", C.c_int32),
-        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("tile_rows", C.c_int32),
         ("a_H", C.c_int32), ("a_W", C.c_int32), ("C", C.c_int32),
         ("a_sw", C.c_int64), ("a_sh", C.c_int64), ("a_sn", C.c_int64),
         ("b", C.c_void_p), ("b_terms", C.c_int32), ("b_term_g", C.c_int32),
-        ("b_groups", C.c_int32), ("b_batched", C.c_int32), ("n_out", C.c_int32),
-        ("b_sn", C.c_int64), ("b_sg", C.c_int64),
+        ("b_groups", C.c_int32), ("b_groups2", C.c_int32), ("b_batched", C.c_int32),
+        ("b_batched_h", C.c_int32), ("n_out", C.c_int32),
+        ("b_sn", C.c_int64), ("b_sg", C.c_int64), ("b_sg2", C.c_int64),
         ("ntaps", C.c_int32),
         ("tap_dy", C.c_int32 * MAX_TAPS), ("tap_dx", C.c_int32 * MAX_TAPS),
         ("tap_img_off", C.c_int32 * MAX_TAPS),

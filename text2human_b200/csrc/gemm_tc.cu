@@ -25,7 +25,7 @@ struct TapGemmDev {
   int TW, TH;  // spatial box of one 128-row block
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int n_out, C, kchunks, nterms;
-  int a_term_imgs, a_bcast, b_term_g, b_batched;
+  int a_term_imgs, a_bcast, b_term_g, b_batched, b_batched_h;
   int ntaps;
   int tap_dy[T2H_MAX_TAPS], tap_dx[T2H_MAX_TAPS], tap_img_off[T2H_MAX_TAPS];
   void* d;
@@ -129,7 +129,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, MBLK, BN);
         const int a_img = P.a_bcast ? 0 : t.img;
-        const int b_g = P.b_batched ? t.img : 0;
+        const int b_g2 = P.b_batched ? t.img : 0;
+        const int b_g = P.b_batched_h ? t.h0 : 0;
         for (int tap = 0; tap < P.ntaps; ++tap) {
           const int dy = P.tap_dy[tap], dx = P.tap_dx[tap], ioff = P.tap_img_off[tap];
           for (int ch = 0; ch < P.kchunks; ++ch) {
@@ -143,8 +144,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int mb = 0; mb < MBLK; ++mb)
                 tma_load_4d(&tmA, &full_bar[stage], sa + mb * kABlockBytes, ch * kBK, t.w0 + dx,
                             t.h0 + mb * P.TH + dy, a_img + ioff + ta);
-              tma_load_3d(&tmB, &full_bar[stage], sa + MBLK * kABlockBytes, ch * kBK, t.n0,
-                          b_g + tap + tb);
+              tma_load_4d(&tmB, &full_bar[stage], sa + MBLK * kABlockBytes, ch * kBK, t.n0,
+                          b_g + tap + tb, b_g2);
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -394,13 +395,14 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   T2H_CHECK_ARG(p->d_mode == T2H_OUT_F32 || p->residual == nullptr,
                 "tapgemm: residual add needs fp32 output");
   T2H_CHECK_ARG(p->bias_mode == T2H_BIAS_NONE || p->bias != nullptr, "tapgemm: bias_mode without bias");
+  T2H_CHECK_ARG(!p->b_batched_h || p->H == 1 || p->tile_rows, "tapgemm: b_batched_h needs row tiles");
   T2H_CHECK_ARG(p->gn_stats == nullptr, "tapgemm: fused GroupNorm statistics not implemented yet");
 
   TapGemmDev P;
   P.n_img = p->n_img; P.H = p->H; P.W = p->W;
   P.n_out = p->n_out; P.C = p->C; P.kchunks = (p->C + kBK - 1) / kBK; P.nterms = p->nterms;
   P.a_term_imgs = p->a_term_imgs; P.a_bcast = p->a_bcast;
-  P.b_term_g = p->b_term_g; P.b_batched = p->b_batched;
+  P.b_term_g = p->b_term_g; P.b_batched = p->b_batched; P.b_batched_h = p->b_batched_h;
   P.ntaps = p->ntaps;
   for (int i = 0; i < T2H_MAX_TAPS; ++i) {
     P.tap_dy[i] = i < p->ntaps ? p->tap_dy[i] : 0;
@@ -415,7 +417,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   // ---- tile shape
   // one 128-row block = TH x TW output positions of one image
   int TW, TH;
-  if (p->H == 1) {
+  if (p->H == 1 || p->tile_rows) {
     TW = 128; TH = 1;
   } else {
     TW = 16;
@@ -425,7 +427,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   int BN = 16;
   while (BN < p->n_out && BN < 256) BN <<= 1;
   int MBLK = 1;
-  if (BN == 128 && p->H >= 2 * TH) {
+  if (BN == 128 && p->H >= 2 * TH && !p->tile_rows) {
     long long tiles1 = (long long)p->n_img * ceil_div(p->H, TH) * ceil_div(p->W, TW);
     if (tiles1 >= 4LL * num_sms()) MBLK = 2;
   }
@@ -455,10 +457,12 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)p->C, (uint64_t)p->n_out, (uint64_t)p->b_groups};
-    uint64_t str[3] = {1, (uint64_t)p->b_sn, (uint64_t)p->b_sg};
-    uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
-    int rc = make_tmap(&tmB, p->b, 3, dims, str, box, "tapgemm B");
+    const int g2 = p->b_groups2 > 0 ? p->b_groups2 : 1;
+    uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->n_out, (uint64_t)p->b_groups, (uint64_t)g2};
+    uint64_t str[4] = {1, (uint64_t)p->b_sn, (uint64_t)p->b_sg,
+                       (uint64_t)(g2 > 1 ? p->b_sg2 : p->b_sg)};
+    uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
+    int rc = make_tmap(&tmB, p->b, 4, dims, str, box, "tapgemm B");
     if (rc) return rc;
   }
 

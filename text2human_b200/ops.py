@@ -42,6 +42,28 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ----------------------------------------------------------------------------
+# launch accounting (bench.py reads these; not used for control flow)
+# ----------------------------------------------------------------------------
+COUNTERS = {"launches": 0}
+_PROFILE = {"on": False, "records": []}
+
+
+def _count(n=1):
+    COUNTERS["launches"] += n
+
+
+def profile_tapgemm(on):
+    """When on, every t2h_tapgemm launch is bracketed by CUDA events on the launching stream and
+    recorded as (algorithmic_flops, issued_flops, start_event, end_event)."""
+    _PROFILE["on"] = bool(on)
+    _PROFILE["records"] = []
+
+
+def profile_records():
+    return _PROFILE["records"]
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -67,7 +89,8 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
-             d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None):
+             d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -75,9 +98,11 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.a = a.data_ptr(); p.a_terms = T; p.a_term_imgs = a_term_imgs; p.a_imgs = a_imgs
     p.a_bcast = a_bcast
     p.n_img, p.H, p.W, p.a_H, p.a_W, p.C = n_img, H, W, a_H, a_W, Cc
+    p.tile_rows = tile_rows
     p.a_sw, p.a_sh, p.a_sn = a_sw, a_sh, a_sn
     p.b = b.data_ptr(); p.b_terms = Tb; p.b_term_g = b_term_g; p.b_groups = b_groups
     p.b_batched = b_batched; p.n_out = n_out; p.b_sn = b_sn; p.b_sg = b_sg
+    p.b_groups2 = b_groups2; p.b_sg2 = b_sg2 if b_groups2 > 1 else b_sg; p.b_batched_h = b_batched_h
     p.ntaps = len(taps)
     for i, (dy, dx, off) in enumerate(taps):
         p.tap_dy[i], p.tap_dx[i], p.tap_img_off[i] = dy, dx, off
@@ -93,6 +118,16 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.residual = residual.data_ptr() if residual is not None else None
     p.gn_stats = None
     p.gn_cpg = 0
+    _count()
+    if _PROFILE["on"]:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.t2h_tapgemm(C.byref(p), _stream()))
+        e1.record()
+        algo = 2.0 * n_img * H * W * n_out * Cc * len(taps)
+        _PROFILE["records"].append((algo, algo * p.nterms, e0, e1))
+        return
     _lib.check(lib.t2h_tapgemm(C.byref(p), _stream()))
 
 
@@ -173,18 +208,56 @@ def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False):
     assert (Ga == G) or (a_bcast and Ga == 1)
     out = _alloc_out((G, M, N), planes_out, T, a.device)
     a_sn = a.stride(1)
-    b_sg = b.stride(1)
     a_term_imgs = 1 if T == 1 else a.stride(0) // a_sn
-    b_term_g = 1 if Tb == 1 else b.stride(0) // b_sg
     assert T == 1 or a.stride(0) % a_sn == 0
-    assert Tb == 1 or b.stride(0) % b_sg == 0
     _tapgemm(a=a, a_term_imgs=a_term_imgs, a_imgs=(T - 1) * a_term_imgs + Ga, a_bcast=1 if a_bcast else 0,
              n_img=G, H=1, W=M, a_H=1, a_W=M, Cc=K, a_sw=a.stride(2), a_sh=a_sn, a_sn=a_sn,
-             b=b, b_term_g=b_term_g, b_groups=(Tb - 1) * b_term_g + G, b_batched=1, n_out=N,
-             b_sn=b.stride(2), b_sg=b_sg,
+             b=b, b_term_g=1, b_groups=Tb, b_sg=b.stride(0), b_groups2=G, b_sg2=b.stride(1), b_batched=1,
+             n_out=N, b_sn=b.stride(2),
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
              d_strides=(M * N, 0, N, 1), d_plane=G * M * N,
              bias=bias_row, bias_mode=BIAS_ROW, alpha=alpha)
+    return out
+
+
+def mha_scores(qk, B, Tn, nh, alpha=1.0):
+    """Multi-head q @ k^T without head transposes (transformer_arch.py:41-58).
+    qk: planes [T, B*Tn, 2C] holding q in columns [0,C) and k in [C,2C), heads side by side.
+    -> fp32 [B, nh, Tn, Tn].  (h, img) of the tap-GEMM act as (batch, head)."""
+    _need_cuda(qk)
+    T, M, C2 = qk.shape
+    Cc = C2 // 2
+    hs = Cc // nh
+    assert M == B * Tn and qk.is_contiguous()
+    out = torch.empty((B, nh, Tn, Tn), dtype=torch.float32, device=qk.device)
+    plane = qk.stride(0)
+    assert plane % hs == 0
+    kview = qk[:, :, Cc:]
+    _tapgemm(a=qk, a_term_imgs=plane // hs, a_imgs=(T - 1) * (plane // hs) + nh, a_bcast=0,
+             n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=hs, a_sw=C2, a_sh=Tn * C2, a_sn=hs, tile_rows=1,
+             b=kview, b_term_g=B, b_groups=T * B, b_sg=Tn * C2, b_batched_h=1,
+             b_groups2=nh, b_sg2=hs, b_batched=1, n_out=Tn, b_sn=C2,
+             taps=_TAPS_1, d=out, d_mode=OUT_F32, d_strides=(Tn * Tn, nh * Tn * Tn, Tn, 1), alpha=alpha)
+    return out
+
+
+def mha_pv(p, vt, B, Tn, nh):
+    """Multi-head att @ v (transformer_arch.py:65-67).  p: planes [T,B,nh,Tn,Tn];
+    vt: planes [T,B,C,Tn] (v transposed: channels x tokens).  -> planes [T, B*Tn, C] with the
+    heads re-assembled side by side."""
+    _need_cuda(p, vt)
+    T = p.shape[0]
+    Cc = vt.shape[2]
+    hs = Cc // nh
+    assert p.is_contiguous() and vt.is_contiguous()
+    out = torch.empty((T, B * Tn, Cc), dtype=torch.float16, device=p.device)
+    _tapgemm(a=p, a_term_imgs=B * nh, a_imgs=T * B * nh, a_bcast=0,
+             n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=Tn, a_sw=Tn, a_sh=nh * Tn * Tn, a_sn=Tn * Tn,
+             tile_rows=1,
+             b=vt, b_term_g=B, b_groups=T * B, b_sg=Cc * Tn, b_batched_h=1,
+             b_groups2=nh, b_sg2=hs * Tn, b_batched=1, n_out=hs, b_sn=Tn,
+             taps=_TAPS_1, d=out, d_mode=OUT_PLANES, d_strides=(hs, Tn * Cc, Cc, 1),
+             d_plane=out.stride(0))
     return out
 
 
@@ -227,6 +300,7 @@ def nchw_to_planes(x, c_pad=None, terms=None):
     terms = terms or get_terms()
     cp = c_pad if c_pad is not None else (Cc + 7) // 8 * 8
     out = torch.empty((terms, N, H, W, cp), dtype=torch.float16, device=x.device)
+    _count(1)
     _lib.check(_lib.load().t2h_nchw_to_planes(_ptr(x), _ptr(out), N, Cc, H, W, cp, terms, _stream()))
     return out
 
@@ -235,6 +309,7 @@ def nhwc_to_nchw(x):
     _need_cuda(x)
     N, H, W, Cc = x.shape
     out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
+    _count(1)
     _lib.check(_lib.load().t2h_nhwc_to_nchw(_ptr(x), _ptr(out), N, Cc, H, W, _stream()))
     return out
 
@@ -244,6 +319,7 @@ def nchw_to_nhwc(x):
     x = _f32c(x)
     N, Cc, H, W = x.shape
     out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=x.device)
+    _count(1)
     _lib.check(_lib.load().t2h_nchw_to_nhwc(_ptr(x), _ptr(out), N, Cc, H, W, _stream()))
     return out
 
@@ -261,6 +337,7 @@ def f32_to_planes(x, mode=CVT_PLAIN, terms=None):
     else:
         shape = (terms, N, H, W, Cc)
     out = torch.empty(shape, dtype=torch.float16, device=x.device)
+    _count(1)
     _lib.check(_lib.load().t2h_f32_to_planes(_ptr(x), _ptr(out), N, H, W, Cc, mode, terms, _stream()))
     return out
 
@@ -272,6 +349,7 @@ def group_norm(x, gamma, beta, *, swish, groups=32, eps=1e-6, terms=None):
     terms = terms or get_terms()
     lib = _lib.load()
     stats = torch.zeros((N, groups, 2), dtype=torch.float64, device=x.device)
+    _count(2)
     _lib.check(lib.t2h_gn_stats(_ptr(x), _ptr(stats), N, H * W, Cc, groups, _stream()))
     out = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device)
     _lib.check(lib.t2h_gn_apply(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), N, H * W, Cc,
@@ -282,6 +360,7 @@ def group_norm(x, gamma, beta, *, swish, groups=32, eps=1e-6, terms=None):
 def add_inplace(x, y):
     _need_cuda(x, y)
     assert x.shape == y.shape and x.is_contiguous() and y.is_contiguous()
+    _count(1)
     _lib.check(_lib.load().t2h_add_inplace(_ptr(x), _ptr(y), x.numel(), _stream()))
     return x
 
@@ -293,6 +372,7 @@ def softmax_rows(s, scale=1.0, terms=None):
     cols = s.shape[-1]
     rows = s.numel() // cols
     out = torch.empty((terms,) + tuple(s.shape), dtype=torch.float16, device=s.device)
+    _count(1)
     _lib.check(_lib.load().t2h_softmax_rows(_ptr(s), _ptr(out), rows, cols, scale, terms, _stream()))
     return out
 
@@ -303,6 +383,7 @@ def layer_norm(x, gamma, beta, eps=1e-5, terms=None):
     terms = terms or get_terms()
     rows, Cc = x.shape
     out = torch.empty((terms, rows, Cc), dtype=torch.float16, device=x.device)
+    _count(1)
     _lib.check(_lib.load().t2h_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, Cc, eps, terms,
                                          _stream()))
     return out
@@ -313,6 +394,7 @@ def embed_sum(idx, segm, tex, tok_emb, pos_emb, segm_emb, tex_emb):
     B, T = idx.shape
     Cc = tok_emb.shape[1]
     x = torch.empty((B * T, Cc), dtype=torch.float32, device=idx.device)
+    _count(1)
     _lib.check(_lib.load().t2h_embed_sum(_ptr(idx.contiguous()), _ptr(segm.contiguous()),
                                          _ptr(tex.contiguous()), _ptr(tok_emb), _ptr(pos_emb),
                                          _ptr(segm_emb), _ptr(tex_emb), _ptr(x), B, T, Cc, _stream()))
@@ -325,6 +407,7 @@ def mask_to_ids(mask, ht, wt):
     mask = _f32c(mask)
     B, _, Hs, Ws = mask.shape
     ids = torch.empty((B, ht, wt), dtype=torch.int32, device=mask.device)
+    _count(1)
     _lib.check(_lib.load().t2h_mask_to_ids(_ptr(mask), _ptr(ids), B, Hs, Ws, ht, wt, _stream()))
     return ids
 
@@ -352,6 +435,7 @@ def vq_search(z_nhwc, codebook, book_id, *, ps=1, cont_stride=None, want_list=Tr
     sqerr = torch.zeros((1,), dtype=torch.float64, device=dev) if want_err else None
     wsb = lib.t2h_vq_workspace_bytes(rows, n_books, n_e)
     ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    _count(3)
     _lib.check(lib.t2h_vq_search(_ptr(z_nhwc), _ptr(codebook), _ptr(book_id), B, Hz, Wz, Cz, ps, n_books,
                                  n_e, n_e if cont_stride is None else cont_stride, _ptr(idx),
                                  _ptr(idx_cont), _ptr(idx_list), _ptr(zq_nhwc), _ptr(zq_nchw), _ptr(sqerr),
@@ -366,6 +450,7 @@ def vq_gather(codebook, idx, book_id, *, B, Hz, Wz, Cz, ps=1, want_nchw=True, wa
     dev = codebook.device
     zq_nhwc = torch.empty((B, Hz, Wz, Cz), dtype=torch.float32, device=dev) if want_nhwc else None
     zq_nchw = torch.empty((B, Cz, Hz, Wz), dtype=torch.float32, device=dev) if want_nchw else None
+    _count(1)
     _lib.check(_lib.load().t2h_vq_gather(_ptr(codebook), _ptr(idx.contiguous()), _ptr(book_id), B, Hz, Wz,
                                          Cz, ps, n_books, n_e, _ptr(zq_nhwc), _ptr(zq_nchw), _stream()))
     return zq_nhwc, zq_nchw

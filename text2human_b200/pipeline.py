@@ -1,0 +1,206 @@
+"""Wrapper-level sequences of the Text2Human hot path on the B200 kernels.
+
+Mirrors the inference methods of the reference's model wrappers (same method
+names and ``opt`` keys), chaining the arch modules through their NHWC entry
+points so no layout round trip happens between encoder, quantizer and decoder:
+
+  VQImageSegmTextureModel.encode/decode/forward_step   models/vqgan_model.py:532-551
+  HierarchyVQSpatialTextureAwareModel.top_encode/bot_encode/decode/forward_step
+                                                       models/hierarchy_vqgan_model.py:215-239
+  BaseSampleModel.sample_fn                            models/sample_model.py:256-328
+
+Training-only members of the reference wrappers (losses, optimisers, LPIPS,
+discriminator, logging) are outside this round's scope.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .transformer_arch import TransformerMultiHead
+from .vqgan_arch import (Decoder, DecoderRes, Encoder, VectorQuantizer, VectorQuantizerSpatialTextureAware,
+                         VectorQuantizerTexture, conv1x1_nhwc)
+
+
+class VQImageSegmTextureModel(nn.Module):
+    """top-level VQGAN: Encoder -> 1x1 -> VectorQuantizerTexture -> 1x1 -> Decoder
+    (constructor keys as configs/vqvae_top.yml; reference vqgan_model.py:389-422)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.encoder = Encoder(ch=opt['ch'], num_res_blocks=opt['num_res_blocks'],
+                               attn_resolutions=opt['attn_resolutions'], ch_mult=opt['ch_mult'],
+                               in_channels=opt['in_channels'], resolution=opt['resolution'],
+                               z_channels=opt['z_channels'], double_z=opt['double_z'],
+                               dropout=opt['dropout'])
+        self.decoder = Decoder(in_channels=opt['in_channels'], resolution=opt['resolution'],
+                               z_channels=opt['z_channels'], ch=opt['ch'], out_ch=opt['out_ch'],
+                               num_res_blocks=opt['num_res_blocks'],
+                               attn_resolutions=opt['attn_resolutions'], ch_mult=opt['ch_mult'],
+                               dropout=opt['dropout'], resamp_with_conv=True, give_pre_end=False)
+        self.quantize = VectorQuantizerTexture(opt['n_embed'], opt['embed_dim'], beta=0.25)
+        self.quant_conv = torch.nn.Conv2d(opt["z_channels"], opt['embed_dim'], 1)
+        self.post_quant_conv = torch.nn.Conv2d(opt['embed_dim'], opt["z_channels"], 1)
+
+    @torch.no_grad()
+    def encode_nhwc(self, x, mask):
+        h = self.encoder.forward_nhwc(x)
+        h = conv1x1_nhwc(h, self.quant_conv)
+        return self.quantize.forward_nhwc(h, mask), h
+
+    @torch.no_grad()
+    def encode(self, x, mask):
+        r, _ = self.encode_nhwc(x, mask)
+        quant = ops.nhwc_to_nchw(r["zq_nhwc"])
+        return quant, r["loss"], (None, r["idx_cont"], list(r["idx_list"].unbind(0)))
+
+    @torch.no_grad()
+    def decode(self, quant):
+        return self.decoder.forward_nhwc(conv1x1_nhwc(ops.nchw_to_nhwc(quant), self.post_quant_conv))
+
+    @torch.no_grad()
+    def forward_step(self, input, mask, return_info=False):
+        r, z = self.encode_nhwc(input, mask)
+        dec = self.decoder.forward_nhwc(conv1x1_nhwc(r["zq_nhwc"], self.post_quant_conv))
+        if return_info:
+            return dec, r["loss"], dict(idx_cont=r["idx_cont"], idx_list=r["idx_list"], z_nhwc=z,
+                                        zq_nhwc=r["zq_nhwc"])
+        return dec, r["loss"]
+
+
+class HierarchyVQSpatialTextureAwareModel(nn.Module):
+    """two-level VQGAN (constructor keys as configs/vqvae_bottom.yml;
+    reference hierarchy_vqgan_model.py:24-85)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.top_encoder = Encoder(ch=opt['top_ch'], num_res_blocks=opt['top_num_res_blocks'],
+                                   attn_resolutions=opt['top_attn_resolutions'], ch_mult=opt['top_ch_mult'],
+                                   in_channels=opt['top_in_channels'], resolution=opt['top_resolution'],
+                                   z_channels=opt['top_z_channels'], double_z=opt['top_double_z'],
+                                   dropout=opt['top_dropout'])
+        self.decoder = Decoder(in_channels=opt['top_in_channels'], resolution=opt['top_resolution'],
+                               z_channels=opt['top_z_channels'], ch=opt['top_ch'], out_ch=opt['top_out_ch'],
+                               num_res_blocks=opt['top_num_res_blocks'],
+                               attn_resolutions=opt['top_attn_resolutions'], ch_mult=opt['top_ch_mult'],
+                               dropout=opt['top_dropout'], resamp_with_conv=True, give_pre_end=False)
+        self.top_quantize = VectorQuantizerTexture(1024, opt['embed_dim'], beta=0.25)
+        self.top_quant_conv = torch.nn.Conv2d(opt["top_z_channels"], opt['embed_dim'], 1)
+        self.top_post_quant_conv = torch.nn.Conv2d(opt['embed_dim'], opt["top_z_channels"], 1)
+
+        self.bot_encoder = Encoder(ch=opt['bot_ch'], num_res_blocks=opt['bot_num_res_blocks'],
+                                   attn_resolutions=opt['bot_attn_resolutions'], ch_mult=opt['bot_ch_mult'],
+                                   in_channels=opt['bot_in_channels'], resolution=opt['bot_resolution'],
+                                   z_channels=opt['bot_z_channels'], double_z=opt['bot_double_z'],
+                                   dropout=opt['bot_dropout'])
+        self.bot_decoder_res = DecoderRes(in_channels=opt['bot_in_channels'],
+                                          resolution=opt['bot_resolution'],
+                                          z_channels=opt['bot_z_channels'], ch=opt['bot_ch'],
+                                          num_res_blocks=opt['bot_num_res_blocks'],
+                                          ch_mult=opt['bot_ch_mult'], dropout=opt['bot_dropout'],
+                                          give_pre_end=False)
+        self.bot_quantize = VectorQuantizerSpatialTextureAware(
+            opt['bot_n_embed'], opt['embed_dim'], beta=0.25, spatial_size=opt['codebook_spatial_size'])
+        self.bot_quant_conv = torch.nn.Conv2d(opt["bot_z_channels"], opt['embed_dim'], 1)
+        self.bot_post_quant_conv = torch.nn.Conv2d(opt['embed_dim'], opt["bot_z_channels"], 1)
+
+    @torch.no_grad()
+    def top_encode_nhwc(self, x, mask):
+        h = conv1x1_nhwc(self.top_encoder.forward_nhwc(x), self.top_quant_conv)
+        r = self.top_quantize.forward_nhwc(h, mask)
+        return conv1x1_nhwc(r["zq_nhwc"], self.top_post_quant_conv), r
+
+    @torch.no_grad()
+    def bot_encode_nhwc(self, x, mask):
+        h = conv1x1_nhwc(self.bot_encoder.forward_nhwc(x), self.bot_quant_conv)
+        r = self.bot_quantize.forward_nhwc(h, mask)
+        quant = conv1x1_nhwc(r["zq_nhwc"], self.bot_post_quant_conv)
+        return self.bot_decoder_res.forward_nhwc(quant), r
+
+    @torch.no_grad()
+    def top_encode(self, x, mask):
+        return ops.nhwc_to_nchw(self.top_encode_nhwc(x, mask)[0])
+
+    @torch.no_grad()
+    def bot_encode(self, x, mask):
+        res, r = self.bot_encode_nhwc(x, mask)
+        return ops.nhwc_to_nchw(res), r["loss"], (None, r["idx_cont"].reshape(-1), list(r["idx_list"].unbind(0)))
+
+    @torch.no_grad()
+    def decode(self, quant_top, bot_dec_res):
+        return self.decoder(quant_top, bot_h=bot_dec_res)
+
+    @torch.no_grad()
+    def forward_step(self, input, mask, return_info=False):
+        quant_top, rt = self.top_encode_nhwc(input, mask)
+        bot_dec_res, rb = self.bot_encode_nhwc(input, mask)
+        dec = self.decoder.forward_nhwc(quant_top, bot_h=bot_dec_res)
+        if return_info:
+            return dec, rb["loss"], dict(top_idx=rt["idx_cont"], bot_idx=rb["idx_cont"])
+        return dec, rb["loss"]
+
+    @torch.no_grad()
+    def decode_from_indices(self, top_list, bot_list, mask):
+        """tokens -> image (the decode half of sample_and_refine, sample_model.py:225-243, batched)"""
+        B = mask.shape[0]
+        zt = self.top_quantize.get_codebook_entry(top_list, mask, (B, 32, 16, self.opt["top_z_channels"]),
+                                                  nhwc=True)
+        quant_top = conv1x1_nhwc(zt, self.top_post_quant_conv)
+        zb = self.bot_quantize.get_codebook_entry(bot_list, mask, (B, 32, 16, self.opt["bot_z_channels"]),
+                                                  nhwc=True)
+        res = self.bot_decoder_res.forward_nhwc(conv1x1_nhwc(zb, self.bot_post_quant_conv))
+        return self.decoder.forward_nhwc(quant_top, bot_h=res)
+
+
+class Sampler(nn.Module):
+    """The absorbing-diffusion sampling loop of BaseSampleModel (sample_model.py:256-328) around
+    TransformerMultiHead, without the reference's per-codebook host synchronisations.
+
+    RNG: one ``torch.rand`` per step for the reveal schedule and one ``torch.multinomial`` per step
+    over the logits of each position's own texture head (the reference draws every head for every
+    position and keeps one).  torch's generator is used as the random source only."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.sampler_fn = TransformerMultiHead(
+            codebook_size=opt['codebook_size'], segm_codebook_size=opt['segm_codebook_size'],
+            texture_codebook_size=opt['texture_codebook_size'], bert_n_emb=opt['bert_n_emb'],
+            bert_n_layers=opt['bert_n_layers'], bert_n_head=opt['bert_n_head'], block_size=opt['block_size'],
+            latent_shape=opt['latent_shape'], embd_pdrop=opt['embd_pdrop'], resid_pdrop=opt['resid_pdrop'],
+            attn_pdrop=opt['attn_pdrop'], num_head=opt['num_head'])
+        self.shape = tuple(opt['latent_shape'])
+        self.mask_id = opt['codebook_size']
+        self.sample_steps = opt['sample_steps']
+
+    @torch.no_grad()
+    def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None):
+        """segm_tokens int64 [B, T]; texture_mask float [B,1,H,W] of ids 0..17.
+        Returns (list of 18 int64 [B,T] per-codebook index maps with -1 elsewhere, final x_t)."""
+        m = self.sampler_fn
+        B = segm_tokens.shape[0]
+        T = int(np.prod(self.shape))
+        dev = segm_tokens.device
+        steps = sample_steps or self.sample_steps
+        tex = ops.mask_to_ids(texture_mask, self.shape[0], self.shape[1]).view(B, T).long()
+        x_t = torch.full((B, T), self.mask_id, dtype=torch.long, device=dev)
+        unmasked = torch.zeros((B, T), dtype=torch.bool, device=dev)
+        nh, ncls = m.num_head, m.head_class_num
+        tex_c = tex.clamp(0, nh - 1)
+        gather_idx = tex_c.view(B, T, 1, 1).expand(B, T, 1, ncls)
+        valid_tex = (tex >= 0) & (tex < nh)
+        for t in range(steps, 0, -1):
+            changes = torch.rand((B, T), device=dev, generator=generator) < (1.0 / t)
+            changes = changes & ~unmasked
+            unmasked = unmasked | changes
+            logits = m.forward_logits(x_t, segm_tokens, tex_c)  # [B,T,nh,ncls]
+            own = logits.gather(2, gather_idx).view(B * T, ncls)  # each position's own texture head
+            probs = torch.softmax(own / temp, dim=-1)
+            draw = torch.multinomial(probs, 1, True, generator=generator).view(B, T)
+            upd = changes & valid_tex
+            x_t = torch.where(upd, draw + 1024 * tex_c, x_t)
+        final = torch.where(unmasked & valid_tex, x_t - 1024 * tex_c, torch.full_like(x_t, -1))
+        out = [torch.where(tex == k, final, torch.full_like(final, -1)) for k in range(nh)]
+        return out, x_t

@@ -1,0 +1,185 @@
+"""B200-native mirror of the reference's ``models/archs/transformer_arch.py``.
+
+Same class names, constructor/forward signatures and ``state_dict`` keys as the
+reference.  torch ``nn.Linear`` / ``nn.LayerNorm`` /
+``nn.Embedding`` objects are parameter containers only; the arithmetic runs in
+libt2h: embedding-sum, LayerNorm, tcgen05 GEMMs (fused q|k projection, v^T
+projection, per-head q k^T and att v without head transposes, MLP with fused
+GELU, one N=18*1024 GEMM for the 18 heads), row softmax.
+
+The sampler is always non-causal on the Text2Human path (sampler='absorbing',
+transformer_arch.py:200,30), so no mask and no KV cache exist.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .vqgan_arch import _cached, _f32, _lin_w
+
+
+class CausalSelfAttention(nn.Module):
+    """multi-head self-attention (reference :9-71; runs non-causal)."""
+
+    def __init__(self, bert_n_emb, bert_n_head, attn_pdrop, resid_pdrop, latent_shape, sampler):
+        super().__init__()
+        assert bert_n_emb % bert_n_head == 0
+        self.key = nn.Linear(bert_n_emb, bert_n_emb)
+        self.query = nn.Linear(bert_n_emb, bert_n_emb)
+        self.value = nn.Linear(bert_n_emb, bert_n_emb)
+        self.attn_drop = nn.Dropout(attn_pdrop)
+        self.resid_drop = nn.Dropout(resid_pdrop)
+        self.proj = nn.Linear(bert_n_emb, bert_n_emb)
+        self.n_head = bert_n_head
+        self.causal = True if sampler == 'autoregressive' else False
+        if self.causal:
+            block_size = np.prod(latent_shape)
+            mask = torch.tril(torch.ones(block_size, block_size))
+            self.register_buffer("mask", mask.view(1, 1, block_size, block_size))
+
+    def _qk_packed(self):
+        t = ops.get_terms()
+        w = _cached(self, ("wqk", t), (self.query.weight, self.key.weight),
+                    lambda: ops.pack_linear_weight(torch.cat((self.query.weight, self.key.weight), 0), t))
+        b = _cached(self, ("bqk",), (self.query.bias, self.key.bias),
+                    lambda: torch.cat((self.query.bias, self.key.bias), 0).float().contiguous())
+        return w, b
+
+    def attend(self, hn, x_res, B, T):
+        """hn: LayerNorm'ed planes [Tt, B*T, C]; x_res: fp32 [B*T, C] residual stream.
+        Returns x_res + proj(attention(hn)) as fp32 [B*T, C]."""
+        if self.causal:
+            raise NotImplementedError("sampler='autoregressive' is never used by Text2Human")
+        Tt, M, Cc = hn.shape
+        nh = self.n_head
+        wqk, bqk = self._qk_packed()
+        qk = ops.linear(hn, wqk, bqk, planes_out=True)  # [Tt, M, 2C]  (q | k)
+        vt = ops.bmm_nt(_lin_w(self.value), hn.view(Tt, B, T, Cc), planes_out=True,
+                        bias_row=_f32(self.value.bias), a_bcast=True)  # [Tt, B, C, T]
+        s = ops.mha_scores(qk, B, T, nh)  # fp32 [B, nh, T, T]
+        p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // nh))  # planes [Tt, B, nh, T, T]
+        y = ops.mha_pv(p, vt, B, T, nh)  # planes [Tt, M, C]
+        return ops.linear(y, _lin_w(self.proj), _f32(self.proj.bias), residual=x_res)
+
+    @torch.no_grad()
+    def forward(self, x, layer_past=None):
+        assert layer_past is None, "layer_past is only used by the (unused) autoregressive sampler"
+        B, T, Cc = x.shape
+        x2 = x.reshape(B * T, Cc).float().contiguous()
+        hn = ops.split_planes(x2, ops.get_terms())
+        zero = torch.zeros_like(x2)
+        y = self.attend(hn, zero, B, T).view(B, T, Cc)
+        # `present` (stacked k, v) is built by the reference and discarded by Block (:51, :97-99)
+        return y, None
+
+
+class Block(nn.Module):
+    """pre-LN attention + pre-LN MLP (reference :74-99)."""
+
+    def __init__(self, bert_n_emb, resid_pdrop, bert_n_head, attn_pdrop, latent_shape, sampler):
+        super().__init__()
+        self.ln1 = nn.LayerNorm(bert_n_emb)
+        self.ln2 = nn.LayerNorm(bert_n_emb)
+        self.attn = CausalSelfAttention(bert_n_emb, bert_n_head, attn_pdrop, resid_pdrop, latent_shape,
+                                        sampler)
+        self.mlp = nn.Sequential(
+            nn.Linear(bert_n_emb, 4 * bert_n_emb),
+            nn.GELU(),  # nice
+            nn.Linear(4 * bert_n_emb, bert_n_emb),
+            nn.Dropout(resid_pdrop),
+        )
+
+    def forward_rows(self, x, B, T):
+        """x: fp32 [B*T, C] residual stream -> fp32 [B*T, C]"""
+        h = ops.layer_norm(x, _f32(self.ln1.weight), _f32(self.ln1.bias), self.ln1.eps)
+        x = self.attn.attend(h, x, B, T)
+        h = ops.layer_norm(x, _f32(self.ln2.weight), _f32(self.ln2.bias), self.ln2.eps)
+        m = ops.linear(h, _lin_w(self.mlp[0]), _f32(self.mlp[0].bias), planes_out=True, act=ops.ACT_GELU)
+        return ops.linear(m, _lin_w(self.mlp[2]), _f32(self.mlp[2].bias), residual=x)
+
+    @torch.no_grad()
+    def forward(self, x, layer_past=None, return_present=False):
+        assert layer_past is None
+        B, T, Cc = x.shape
+        y = self.forward_rows(x.reshape(B * T, Cc).float().contiguous(), B, T).view(B, T, Cc)
+        if return_present:
+            return y, None
+        return y
+
+
+class TransformerMultiHead(nn.Module):
+    """the index-prediction transformer with 18 per-texture heads (reference :184-273)."""
+
+    def __init__(self, codebook_size, segm_codebook_size, texture_codebook_size, bert_n_emb, bert_n_layers,
+                 bert_n_head, block_size, latent_shape, embd_pdrop, resid_pdrop, attn_pdrop, num_head,
+                 sampler='absorbing'):
+        super().__init__()
+        self.vocab_size = codebook_size + 1
+        self.n_embd = bert_n_emb
+        self.block_size = block_size
+        self.n_layers = bert_n_layers
+        self.codebook_size = codebook_size
+        self.segm_codebook_size = segm_codebook_size
+        self.texture_codebook_size = texture_codebook_size
+        self.causal = sampler == 'autoregressive'
+        if self.causal:
+            self.vocab_size = codebook_size
+
+        self.tok_emb = nn.Embedding(self.vocab_size, self.n_embd)
+        self.pos_emb = nn.Parameter(torch.zeros(1, self.block_size, self.n_embd))
+        self.segm_emb = nn.Embedding(self.segm_codebook_size, self.n_embd)
+        self.texture_emb = nn.Embedding(self.texture_codebook_size, self.n_embd)
+        self.start_tok = nn.Parameter(torch.zeros(1, 1, self.n_embd))
+        self.drop = nn.Dropout(embd_pdrop)
+
+        self.blocks = nn.Sequential(*[
+            Block(bert_n_emb, resid_pdrop, bert_n_head, attn_pdrop, latent_shape, sampler)
+            for _ in range(self.n_layers)
+        ])
+        self.num_head = num_head
+        self.head_class_num = codebook_size // self.num_head
+        self.ln_f = nn.LayerNorm(self.n_embd)
+        self.head_list = nn.ModuleList(
+            [nn.Linear(self.n_embd, self.head_class_num, bias=False) for _ in range(self.num_head)])
+
+    def get_block_size(self):
+        return self.block_size
+
+    def _init_weights(self, module):
+        # defined but never applied by the reference either (:240, no self.apply)
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+            if isinstance(module, nn.Linear) and module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+
+    def _heads_packed(self):
+        t = ops.get_terms()
+        ws = tuple(h.weight for h in self.head_list)
+        return _cached(self, ("heads", t), ws,
+                       lambda: ops.pack_linear_weight(torch.cat([w.detach() for w in ws], 0), t))
+
+    @torch.no_grad()
+    def forward_logits(self, idx, segm_tokens, texture_tokens):
+        """-> fp32 [B, T, num_head, head_class_num]: all heads from one GEMM"""
+        if self.causal:
+            raise NotImplementedError("sampler='autoregressive' is never used by Text2Human")
+        B, T = idx.shape
+        assert T <= self.block_size, "Cannot forward, model block size is exhausted."
+        x = ops.embed_sum(idx, segm_tokens, texture_tokens, _f32(self.tok_emb.weight),
+                          _f32(self.pos_emb)[0], _f32(self.segm_emb.weight), _f32(self.texture_emb.weight))
+        for block in self.blocks:
+            x = block.forward_rows(x, B, T)
+        h = ops.layer_norm(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), self.ln_f.eps)
+        logits = ops.linear(h, self._heads_packed())  # [B*T, num_head*head_class_num]
+        return logits.view(B, T, self.num_head, self.head_class_num)
+
+    @torch.no_grad()
+    def forward(self, idx, segm_tokens, texture_tokens, t=None):
+        logits = self.forward_logits(idx, segm_tokens, texture_tokens)
+        # reference returns a list of num_head tensors [B, T, head_class_num] (:271-273)
+        return [logits[:, :, i, :] for i in range(self.num_head)]

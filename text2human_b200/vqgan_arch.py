@@ -599,7 +599,8 @@ class VectorQuantizerSpatialTextureAware(_TextureQuantizerBase):
     def forward(self, z, segm_map, temp=None, rescale_logits=False, return_logits=False):
         _check_gumbel_args(temp, rescale_logits, return_logits)
         r = self.forward_nhwc(ops.nchw_to_nhwc(z), segm_map, want_nchw=True)
-        return r["zq_nchw"], r["loss"], (None, r["idx_cont"], list(r["idx_list"].unbind(0)))
+        # unlike the top quantizer, the reference returns the continual indices flat here (:460)
+        return r["zq_nchw"], r["loss"], (None, r["idx_cont"].reshape(-1), list(r["idx_list"].unbind(0)))
 
     @torch.no_grad()
     def get_codebook_entry(self, indices_list, segm_map, shape, nhwc=False):
