@@ -208,3 +208,29 @@ def test_quantizer_edge_cases(cuda):
     assert got["idx_cont"].view(-1).tolist() == [3, 9, -1, -1]
     assert torch.equal(got["zq_nhwc"][0, 1].cpu(), torch.zeros(2, 16))  # unselected rows -> 0
     assert np.array_equal(got["idx_list"].cpu().numpy(), want["idx_list"])
+
+
+@pytest.mark.parametrize("C,Cout,H,W", [(64, 128, 32, 16), (128, 256, 16, 8), (64, 64, 40, 24), (256, 512, 8, 4)])
+def test_fused_groupnorm_statistics_in_conv_epilogue(cuda, C, Cout, H, W):
+    """the conv epilogue's (sum, sumsq) per (image, group) equal those of its own fp32 output"""
+    from text2human_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(C + Cout + H)
+    x = torch.randn(3, C, H, W, device=cuda, generator=g)
+    w = torch.randn(Cout, C, 3, 3, device=cuda, generator=g) / (9 * C) ** 0.5
+    b = torch.randn(Cout, device=cuda, generator=g)
+    res = torch.randn(3, H, W, Cout, device=cuda, generator=g)
+    a = ops.nchw_to_planes(x, terms=2)
+    out, stats = ops.conv3x3(a, ops.pack_conv_weight(w, 2), b, residual=res, want_stats=True)
+    assert stats is not None and stats.shape == (3, 32, 2)
+    o = out.double().view(3, H * W, 32, Cout // 32)
+    want = torch.stack((o.sum((1, 3)), (o * o).sum((1, 3))), -1)
+    assert _rel(stats, want) < 1e-5
+    # and GroupNorm fed with them matches GroupNorm that measures its own statistics
+    gm, bt = torch.randn(Cout, device=cuda, generator=g), torch.randn(Cout, device=cuda, generator=g)
+    a1 = ops.group_norm(out, gm, bt, swish=True, terms=2, stats=stats)
+    a2 = ops.group_norm(out, gm, bt, swish=True, terms=2)
+    assert _rel(_sum(a1), _sum(a2)) < 1e-5
+    # 1x1 conv (spatial tiles) and stride-2 conv epilogues too
+    o1, s1 = ops.conv1x1(a, ops.pack_linear_weight(w[:, :, 1, 1].contiguous(), 2), b, want_stats=True)
+    o1d = o1.double().view(3, H * W, 32, Cout // 32)
+    assert _rel(s1, torch.stack((o1d.sum((1, 3)), (o1d * o1d).sum((1, 3))), -1)) < 1e-5

@@ -1,11 +1,13 @@
 // t2h_tapgemm: persistent, warp-specialised tcgen05 implicit-GEMM for sm_100a.
 //
 //   warp 0   TMA producer   cp.async.bulk.tensor (4-D activation boxes with
-//                           zero OOB fill = conv padding; 3-D weight boxes)
+//                           zero OOB fill = conv padding; 4-D weight boxes)
 //   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16),
 //                           accumulators live in tensor memory, double-buffered
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      tcgen05.ld -> alpha/bias/GELU/residual -> global
+//   warps 4-7 epilogue      tcgen05.ld -> alpha/bias/GELU/residual/GroupNorm
+//                           partial sums -> swizzled smem staging -> TMA store
+//                           (residual tiles arrive by TMA load into smem)
 //
 // The contraction loop runs over (tap, 64-channel chunk, product term).  A tap
 // is a spatial shift of the activation box (3x3 conv = 9 taps, 1x1/Linear/bmm
@@ -20,6 +22,8 @@
 
 namespace t2h {
 
+enum { EPI_DIRECT = 0, EPI_TMA_F32 = 1, EPI_TMA_PLANES = 2 };
+
 struct TapGemmDev {
   int n_img, H, W;
   int TW, TH;  // spatial box of one 128-row block
@@ -29,31 +33,36 @@ struct TapGemmDev {
   int ntaps;
   int tap_dy[T2H_MAX_TAPS], tap_dx[T2H_MAX_TAPS], tap_img_off[T2H_MAX_TAPS];
   void* d;
-  int d_mode, d_terms, vec_ok;
+  int d_mode, d_terms, epi_mode, d_term_imgs;
   long long d_plane, d_sn, d_sh, d_sw, d_sc;
   const float* bias;
   int bias_mode, act;
   float alpha;
   const float* residual;
   double* gn_stats;
-  int gn_cpg;
+  int gn_cpg, gn_groups;
 };
 
-constexpr int kBK = 64;              // fp16 elements per 128-byte swizzled row
-constexpr int kABlockBytes = 128 * 128;  // one 128-row A block of a stage
+constexpr int kBK = 64;                      // fp16 elements per 128-byte swizzled row
+constexpr int kABlockBytes = 128 * 128;      // one 128-row A block of a stage
 constexpr int kThreads = 256;
+constexpr int kEpiBufBytes = 128 * 128;      // one staging tile: 128 rows x 128 bytes
+constexpr int kEpiBytes = 4 * kEpiBufBytes;  // 2 output + 2 residual staging tiles
 
 template <int BN, int MBLK>
 struct Cfg {
   static constexpr int kStageBytes = MBLK * kABlockBytes + BN * 128;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  // 227 KB opt-in limit minus alignment slack, epilogue staging and ~3 KB of static shared memory
+  static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - 4096;
+  static constexpr int kStagesRaw = kBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kAccCols = MBLK * BN;
   static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : (2 * kAccCols);
-  static constexpr int kChunk = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+  static constexpr int kChunk = BN < 32 ? BN : 32;  // columns per tcgen05.ld in the direct epilogue
   // >= 120 KB so that at most one CTA (and one TMEM allocation) lives on an SM
-  static constexpr int kSmemBytes =
-      (kStages * kStageBytes + 1024) < 120 * 1024 ? 120 * 1024 : (kStages * kStageBytes + 1024);
+  static constexpr int kSmemRaw = kStages * kStageBytes + kEpiBytes + 1024;
+  static constexpr int kSmemBytes = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kTmemCols <= 512, "accumulators exceed tensor memory");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
 };
@@ -77,21 +86,70 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmDev& P, int tile, 
   return t;
 }
 
+// byte offset of 16-byte chunk j of row r inside a 128B-swizzled [128 rows][128 bytes] tile
+__device__ __forceinline__ int swz(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+// Per-warp reduction of 2*NG per-thread partial sums (NG groups x {sum, sumsq}) over the 32 rows
+// a warp holds, using a halving butterfly (2*NG-1 + log shuffles), then shared-memory atomics.
+template <int NG>
+__device__ __forceinline__ void gn_accumulate(const float (&v)[32], bool row_ok, int ncols_valid,
+                                              float* gs, int lane) {
+  constexpr int W = 32 / NG;
+  constexpr int NV = 2 * NG;
+  float vals[NV];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const int c = g * W + i;
+      const float x = (row_ok && c < ncols_valid) ? v[c] : 0.f;
+      s += x;
+      ss += x * x;
+    }
+    vals[2 * g] = s;
+    vals[2 * g + 1] = ss;
+  }
+  int idx = 0;
+  int step = 0;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, ++step) {
+    const int off = 1 << step;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? vals[i] : vals[i + n / 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      const float keep = upper ? vals[i + n / 2] : vals[i];
+      vals[i] = keep + recv;
+    }
+    idx |= (upper ? 1 : 0) * (n / 2);
+  }
+#pragma unroll
+  for (int off = NV; off < 32; off <<= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+  if (lane < NV) atomicAdd(&gs[idx], vals[0]);
+}
+
 template <int BN, int MBLK>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ TapGemmDev P) {
   using C = Cfg<BN, MBLK>;
   constexpr int STAGES = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* out_buf = smem + STAGES * C::kStageBytes;  // 2 tiles
+  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;      // 2 tiles
 
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t res_bar[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float gsum[2][2 * 128];  // GroupNorm partial sums of the current / previous tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +157,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (P.epi_mode != EPI_DIRECT) tma_prefetch_desc(&tmD);
+    if (P.epi_mode == EPI_TMA_F32 && P.residual) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -108,6 +168,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
+      mbar_init(&res_bar[s], 1);
     }
     fence_mbar_init();
   }
@@ -115,6 +176,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(&tmem_base_s, C::kTmemCols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 2 * 2 * 128; i += kThreads) (&gsum[0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,62 +257,226 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    constexpr int CH = C::kChunk;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int th = row / P.TW, tw = row - th * P.TW;
+    const bool elected = (threadIdx.x == 128);
     int as = 0, ap = 0;
+    int buf = 0;  // staging buffer toggle (persists across tiles)
+    uint32_t res_par[2] = {0, 0};
+    int tile_par = 0;  // gsum buffer of this tile
+
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile, MBLK, BN);
-      mbar_wait(&tfull_bar[as], ap);
-      tc_fence_after();
-#pragma unroll 1
-      for (int mb = 0; mb < MBLK; ++mb) {
-        const int h = t.h0 + mb * P.TH + th;
-        const int w = t.w0 + tw;
-        const bool row_ok = (h < P.H) && (w < P.W);
-        const long long off = (long long)t.img * P.d_sn + (long long)h * P.d_sh + (long long)w * P.d_sw;
-        const float row_bias = (P.bias_mode == T2H_BIAS_ROW && row_ok) ? P.bias[h * P.W + w] : 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < BN / CH; ++cc) {
-          const int col0 = t.n0 + cc * CH;
-          if (col0 >= P.n_out) break;  // warp-uniform
+
+      if (P.epi_mode == EPI_TMA_F32) {
+        // ---- fp32 NHWC output: 32-column units through swizzled smem + TMA store
+        const int cols_left = P.n_out - t.n0;
+        const int nuc = (cols_left >= BN) ? BN / 32 : (cols_left + 31) / 32;
+        const int nunits = MBLK * nuc;
+        const bool has_res = P.residual != nullptr;
+        auto issue_res = [&](int u, int b) {
+          const int mb = u / nuc, cc = u - mb * nuc;
+          mbar_expect_tx(&res_bar[b], kEpiBufBytes);
+          tma_load_4d(&tmR, &res_bar[b], res_buf + b * kEpiBufBytes, t.n0 + cc * 32, t.w0,
+                      t.h0 + mb * P.TH, t.img);
+        };
+        if (has_res && elected) {
+          issue_res(0, buf);
+          if (nunits > 1) issue_res(1, buf ^ 1);
+        }
+        mbar_wait(&tfull_bar[as], ap);
+        tc_fence_after();
+        for (int u = 0; u < nunits; ++u) {
+          const int mb = u / nuc, cc = u - mb * nuc;
+          const int col0 = t.n0 + cc * 32;
+          const int h = t.h0 + mb * P.TH + th;
+          const int w = t.w0 + tw;
+          const bool row_ok = (h < P.H) && (w < P.W);
           uint32_t r[32];
-          const uint32_t taddr =
-              tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN + cc * CH;
-          if constexpr (CH == 32)
-            tmem_ld_32x32(taddr, r);
-          else
-            tmem_ld_32x16(taddr, r);
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN + cc * 32, r);
           tmem_ld_wait();
-          if (!row_ok) continue;
-          float v[CH];
+          if (u == nunits - 1) {
+            // every TMEM read of this accumulator is done: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          float v[32];
+          const float row_bias =
+              (P.bias_mode == T2H_BIAS_ROW && row_ok) ? __ldg(P.bias + h * P.W + w) : 0.f;
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + row_bias;
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + row_bias;
           if (P.bias_mode == T2H_BIAS_COL) {
 #pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (col0 + i < P.n_out) v[i] += __ldg(P.bias + col0 + i);
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i < P.n_out) {  // n_out % 4 == 0 in this mode
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + i));
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            }
           }
           if (P.act == T2H_ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
           }
-          if (P.d_mode == T2H_OUT_F32) {
-            float* dst = reinterpret_cast<float*>(P.d);
-            if (P.vec_ok) {
+          if (has_res) {
+            mbar_wait(&res_bar[buf], res_par[buf]);
+            res_par[buf] ^= 1;
+            const uint8_t* rb = res_buf + buf * kEpiBufBytes;
 #pragma unroll
-              for (int i = 0; i < CH; i += 4) {
-                if (col0 + i < P.n_out) {
-                  float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                  if (P.residual) {
-                    const float4 rr = *reinterpret_cast<const float4*>(P.residual + off + col0 + i);
-                    o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                  }
-                  *reinterpret_cast<float4*>(dst + off + col0 + i) = o;
+            for (int j = 0; j < 8; ++j) {
+              const float4 rr = *reinterpret_cast<const float4*>(rb + swz(row, j));
+              v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+            }
+          }
+          if (P.gn_stats) {
+            float* gs = &gsum[tile_par][0];
+            const int ncv = P.n_out - col0;
+            switch (P.gn_cpg) {
+              case 2: gn_accumulate<16>(v, row_ok, ncv, gs + 2 * (cc * 16), lane); break;
+              case 4: gn_accumulate<8>(v, row_ok, ncv, gs + 2 * (cc * 8), lane); break;
+              case 8: gn_accumulate<4>(v, row_ok, ncv, gs + 2 * (cc * 4), lane); break;
+              case 16: gn_accumulate<2>(v, row_ok, ncv, gs + 2 * (cc * 2), lane); break;
+              default: gn_accumulate<1>(v, row_ok, ncv, gs + 2 * ((cc * 32) / P.gn_cpg), lane); break;
+            }
+          }
+          named_bar_sync(1, 128);  // out_buf[buf] is free (elected waited for its previous store)
+          uint8_t* ob = out_buf + buf * kEpiBufBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(ob + swz(row, j)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);  // staging tile complete; residual tile fully consumed
+          if (elected) {
+            tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);
+            tma_store_commit();
+            if (has_res && u + 2 < nunits) issue_res(u + 2, buf);
+            tma_store_wait_read<1>();  // the other staging tile is free again
+          }
+          buf ^= 1;
+        }
+        if (P.gn_stats) {
+          // all shared atomics of this tile happened before the last named barrier
+          const int et = threadIdx.x - 128;
+          const int ngt = (BN + P.gn_cpg - 1) / P.gn_cpg;  // groups this tile can touch
+          for (int sl = et; sl < 2 * ngt; sl += 128) {
+            const int g = t.n0 / P.gn_cpg + (sl >> 1);
+            if (g < P.gn_groups)
+              atomicAdd(&P.gn_stats[((long long)t.img * P.gn_groups + g) * 2 + (sl & 1)],
+                        (double)gsum[tile_par][sl]);
+            gsum[tile_par][sl] = 0.f;
+          }
+          tile_par ^= 1;
+        }
+      } else if (P.epi_mode == EPI_TMA_PLANES) {
+        // ---- fp16 plane output: 64-column units, hi and lo tiles staged side by side
+        const int cols_left = P.n_out - t.n0;
+        const int nuc = (cols_left >= BN) ? BN / 64 : (cols_left + 63) / 64;
+        const int nunits = MBLK * nuc;
+        mbar_wait(&tfull_bar[as], ap);
+        tc_fence_after();
+        for (int u = 0; u < nunits; ++u) {
+          const int mb = u / nuc, cc = u - mb * nuc;
+          const int col0 = t.n0 + cc * 64;
+          const int h = t.h0 + mb * P.TH + th;
+          const int w = t.w0 + tw;
+          const bool row_ok = (h < P.H) && (w < P.W);
+          const float row_bias =
+              (P.bias_mode == T2H_BIAS_ROW && row_ok) ? __ldg(P.bias + h * P.W + w) : 0.f;
+          uint8_t* ohi = out_buf;
+          uint8_t* olo = out_buf + kEpiBufBytes;
+          named_bar_sync(1, 128);  // both staging tiles free (elected waited on the previous stores)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN +
+                                   cc * 64 + half * 32;
+            tmem_ld_32x32(taddr, r);
+            tmem_ld_wait();
+            if (u == nunits - 1 && half == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + row_bias;
+            if (P.bias_mode == T2H_BIAS_COL) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (col0 + half * 32 + i < P.n_out) {  // n_out % 8 == 0 in this mode
+                  const float4 b4 =
+                      __ldg(reinterpret_cast<const float4*>(P.bias + col0 + half * 32 + i));
+                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                 }
               }
-            } else {
+            }
+            if (P.act == T2H_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __align__(16) __half hi[8];
+              __align__(16) __half lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split_f16(v[8 * j + e], hi[e], lo[e]);
+              *reinterpret_cast<uint4*>(ohi + swz(row, half * 4 + j)) = *reinterpret_cast<uint4*>(hi);
+              if (P.d_terms == 2)
+                *reinterpret_cast<uint4*>(olo + swz(row, half * 4 + j)) = *reinterpret_cast<uint4*>(lo);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (elected) {
+            tma_store_4d(&tmD, ohi, col0, t.w0, t.h0 + mb * P.TH, t.img);
+            if (P.d_terms == 2)
+              tma_store_4d(&tmD, olo, col0, t.w0, t.h0 + mb * P.TH, t.img + P.d_term_imgs);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+        }
+      } else {
+        // ---- direct path: strided / tiny outputs (NCHW conv_out, n_out < 32, unaligned)
+        constexpr int CH = C::kChunk;
+        mbar_wait(&tfull_bar[as], ap);
+        tc_fence_after();
+#pragma unroll 1
+        for (int mb = 0; mb < MBLK; ++mb) {
+          const int h = t.h0 + mb * P.TH + th;
+          const int w = t.w0 + tw;
+          const bool row_ok = (h < P.H) && (w < P.W);
+          const long long off = (long long)t.img * P.d_sn + (long long)h * P.d_sh + (long long)w * P.d_sw;
+          const float row_bias = (P.bias_mode == T2H_BIAS_ROW && row_ok) ? P.bias[h * P.W + w] : 0.f;
+#pragma unroll 1
+          for (int cc = 0; cc < BN / CH; ++cc) {
+            const int col0 = t.n0 + cc * CH;
+            if (col0 >= P.n_out) break;  // warp-uniform
+            uint32_t r[32];
+            const uint32_t taddr =
+                tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN + cc * CH;
+            if constexpr (CH == 32)
+              tmem_ld_32x32(taddr, r);
+            else
+              tmem_ld_32x16(taddr, r);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            float v[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + row_bias;
+            if (P.bias_mode == T2H_BIAS_COL) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i)
+                if (col0 + i < P.n_out) v[i] += __ldg(P.bias + col0 + i);
+            }
+            if (P.act == T2H_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+            }
+            if (P.d_mode == T2H_OUT_F32) {
+              float* dst = reinterpret_cast<float*>(P.d);
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
                 if (col0 + i < P.n_out) {
@@ -260,24 +486,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   dst[o] = val;
                 }
               }
-            }
-          } else {
-            __half* dst = reinterpret_cast<__half*>(P.d);
-            if (P.vec_ok) {
-#pragma unroll
-              for (int i = 0; i < CH; i += 8) {
-                if (col0 + i < P.n_out) {
-                  __align__(16) __half hi[8];
-                  __align__(16) __half lo[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) split_f16(v[i + e], hi[e], lo[e]);
-                  *reinterpret_cast<uint4*>(dst + off + col0 + i) = *reinterpret_cast<uint4*>(hi);
-                  if (P.d_terms == 2)
-                    *reinterpret_cast<uint4*>(dst + P.d_plane + off + col0 + i) =
-                        *reinterpret_cast<uint4*>(lo);
-                }
-              }
             } else {
+              __half* dst = reinterpret_cast<__half*>(P.d);
 #pragma unroll
               for (int i = 0; i < CH; ++i) {
                 if (col0 + i < P.n_out) {
@@ -291,16 +501,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
-      // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) {
         as = 0;
         ap ^= 1;
       }
     }
+    if (elected) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -329,7 +539,8 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+// elem_bytes: 2 (fp16) or 4 (fp32); strides in elements
+static int make_tmap(CUtensorMap* tm, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                      const uint64_t* strides_elems, const uint32_t* box, const char* what) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   if (!enc) return fail(T2H_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -340,7 +551,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
     bx[i] = box[i];
     es[i] = 1;
     if (i > 0) {
-      gstr[i - 1] = strides_elems[i] * 2;  // bytes
+      gstr[i - 1] = strides_elems[i] * elem_bytes;
       if (gstr[i - 1] % 16 != 0)
         return fail(T2H_EINVAL, "%s: stride of dim %d (%llu bytes) is not a multiple of 16", what, i,
                     (unsigned long long)gstr[i - 1]);
@@ -348,9 +559,10 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
   }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0)
     return fail(T2H_EINVAL, "%s: base pointer not 16-byte aligned", what);
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx,
-                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(T2H_ECUDA,
                 "%s: cuTensorMapEncodeTiled failed (%d) dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]",
@@ -361,8 +573,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t
 }
 
 template <int BN, int MBLK>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmDev& P,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                  const CUtensorMap& tmR, const TapGemmDev& P, cudaStream_t stream) {
   using C = Cfg<BN, MBLK>;
   static bool configured = false;
   if (!configured) {
@@ -371,7 +583,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmD
     configured = true;
   }
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  tapgemm_kernel<BN, MBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, P);
+  tapgemm_kernel<BN, MBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmD, tmR, P);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -396,7 +608,6 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
                 "tapgemm: residual add needs fp32 output");
   T2H_CHECK_ARG(p->bias_mode == T2H_BIAS_NONE || p->bias != nullptr, "tapgemm: bias_mode without bias");
   T2H_CHECK_ARG(!p->b_batched_h || p->H == 1 || p->tile_rows, "tapgemm: b_batched_h needs row tiles");
-  T2H_CHECK_ARG(p->gn_stats == nullptr, "tapgemm: fused GroupNorm statistics not implemented yet");
 
   TapGemmDev P;
   P.n_img = p->n_img; P.H = p->H; P.W = p->W;
@@ -413,6 +624,8 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   P.d_sn = p->d_sn; P.d_sh = p->d_sh; P.d_sw = p->d_sw; P.d_sc = p->d_sc;
   P.bias = p->bias; P.bias_mode = p->bias_mode; P.act = p->act; P.alpha = p->alpha;
   P.residual = p->residual; P.gn_stats = p->gn_stats; P.gn_cpg = p->gn_cpg;
+  P.gn_groups = p->gn_cpg > 0 ? p->n_out / p->gn_cpg : 0;
+  P.d_term_imgs = 0;
 
   // ---- tile shape
   // one 128-row block = TH x TW output positions of one image
@@ -439,21 +652,37 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   T2H_CHECK_ARG(total < (1LL << 31), "tapgemm: too many tiles");
   P.total_tiles = (int)total;
 
-  // ---- vectorised epilogue eligibility
-  const int vw = (p->d_mode == T2H_OUT_F32) ? 4 : 8;
-  bool vec = p->d_sc == 1 && p->n_out % vw == 0 && p->d_sw % vw == 0 && p->d_sh % vw == 0 &&
-             p->d_sn % vw == 0 && (reinterpret_cast<uintptr_t>(p->d) % 16 == 0);
-  if (p->d_mode == T2H_OUT_PLANES && p->d_terms == 2) vec = vec && (p->d_plane % 8 == 0);
-  if (p->residual) vec = vec && (reinterpret_cast<uintptr_t>(p->residual) % 16 == 0);
-  P.vec_ok = vec ? 1 : 0;
+  // ---- epilogue mode
+  const int esz = (p->d_mode == T2H_OUT_F32) ? 4 : 2;
+  const int align_el = 16 / esz;  // elements per 16 bytes
+  bool tma_ok = p->d_sc == 1 && p->n_out % (p->d_mode == T2H_OUT_F32 ? 4 : 8) == 0 &&
+                p->d_sw % align_el == 0 && (reinterpret_cast<uintptr_t>(p->d) % 16 == 0) &&
+                BN >= (p->d_mode == T2H_OUT_F32 ? 32 : 64);
+  // strides of the dims the output domain really uses must be TMA-encodable
+  if (p->H > 1) tma_ok = tma_ok && p->d_sh % align_el == 0 && p->d_sh > 0;
+  if (p->n_img > 1) tma_ok = tma_ok && p->d_sn % align_el == 0 && p->d_sn > 0;
+  if (p->d_mode == T2H_OUT_PLANES && p->d_terms == 2) {
+    // the lo plane is addressed as extra images: its distance must be a whole number of d_sn
+    const long long sn = (p->n_img > 1) ? p->d_sn : p->d_plane;
+    tma_ok = tma_ok && sn > 0 && p->d_plane % sn == 0 && p->d_plane % align_el == 0;
+  }
+  if (p->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->residual) % 16 == 0);
+  if (p->bias_mode == T2H_BIAS_COL) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0);
+  P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
+  if (p->gn_stats) {
+    T2H_CHECK_ARG(P.epi_mode == EPI_TMA_F32, "tapgemm: gn_stats needs an aligned fp32 NHWC output");
+    T2H_CHECK_ARG(p->gn_cpg >= 2 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0,
+                  "tapgemm: gn_cpg=%d must be a power of two >= 2 dividing n_out", p->gn_cpg);
+    T2H_CHECK_ARG(BN % p->gn_cpg == 0 || p->n_out <= BN, "tapgemm: group straddles column tiles");
+  }
 
   // ---- tensor maps
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmD, tmR;
   {
     uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->a_W, (uint64_t)p->a_H, (uint64_t)p->a_imgs};
     uint64_t str[4] = {1, (uint64_t)p->a_sw, (uint64_t)p->a_sh, (uint64_t)p->a_sn};
     uint32_t box[4] = {(uint32_t)kBK, (uint32_t)TW, (uint32_t)TH, 1};
-    int rc = make_tmap(&tmA, p->a, 4, dims, str, box, "tapgemm A");
+    int rc = make_tmap(&tmA, p->a, 2, 4, dims, str, box, "tapgemm A");
     if (rc) return rc;
   }
   {
@@ -462,17 +691,41 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     uint64_t str[4] = {1, (uint64_t)p->b_sn, (uint64_t)p->b_sg,
                        (uint64_t)(g2 > 1 ? p->b_sg2 : p->b_sg)};
     uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
-    int rc = make_tmap(&tmB, p->b, 4, dims, str, box, "tapgemm B");
+    int rc = make_tmap(&tmB, p->b, 2, 4, dims, str, box, "tapgemm B");
     if (rc) return rc;
+  }
+  tmD = tmA;
+  tmR = tmA;
+  if (P.epi_mode != EPI_DIRECT) {
+    // dims the output domain does not use get a harmless, 16-byte-aligned stride
+    const uint64_t sw = (uint64_t)p->d_sw;
+    const uint64_t sh = (p->H > 1) ? (uint64_t)p->d_sh : sw * (uint64_t)p->W;
+    uint64_t sn = (p->n_img > 1) ? (uint64_t)p->d_sn : sh * (uint64_t)p->H;
+    uint64_t imgs = (uint64_t)p->n_img;
+    if (P.epi_mode == EPI_TMA_PLANES && p->d_terms == 2) {
+      if (p->n_img == 1) sn = (uint64_t)p->d_plane;
+      P.d_term_imgs = (int)(p->d_plane / (long long)sn);
+      imgs = (uint64_t)P.d_term_imgs + (uint64_t)p->n_img;
+    }
+    uint64_t dims[4] = {(uint64_t)p->n_out, (uint64_t)p->W, (uint64_t)p->H, imgs};
+    uint64_t str[4] = {1, sw, sh, sn};
+    uint32_t box[4] = {(uint32_t)(esz == 4 ? 32 : 64), (uint32_t)TW, (uint32_t)TH, 1};
+    int rc = make_tmap(&tmD, p->d, esz, 4, dims, str, box, "tapgemm D");
+    if (rc) return rc;
+    if (p->residual) {
+      uint64_t rdims[4] = {(uint64_t)p->n_out, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->n_img};
+      rc = make_tmap(&tmR, p->residual, 4, 4, rdims, str, box, "tapgemm residual");
+      if (rc) return rc;
+    }
   }
 
   cudaStream_t s = as_stream(stream);
-  if (MBLK == 2) return launch<128, 2>(tmA, tmB, P, s);
+  if (MBLK == 2) return launch<128, 2>(tmA, tmB, tmD, tmR, P, s);
   switch (BN) {
-    case 16: return launch<16, 1>(tmA, tmB, P, s);
-    case 32: return launch<32, 1>(tmA, tmB, P, s);
-    case 64: return launch<64, 1>(tmA, tmB, P, s);
-    case 128: return launch<128, 1>(tmA, tmB, P, s);
-    default: return launch<256, 1>(tmA, tmB, P, s);
+    case 16: return launch<16, 1>(tmA, tmB, tmD, tmR, P, s);
+    case 32: return launch<32, 1>(tmA, tmB, tmD, tmR, P, s);
+    case 64: return launch<64, 1>(tmA, tmB, tmD, tmR, P, s);
+    case 128: return launch<128, 1>(tmA, tmB, tmD, tmR, P, s);
+    default: return launch<256, 1>(tmA, tmB, tmD, tmR, P, s);
   }
 }

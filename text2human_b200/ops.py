@@ -90,7 +90,7 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
-             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0):
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -116,8 +116,8 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.act = act
     p.alpha = alpha
     p.residual = residual.data_ptr() if residual is not None else None
-    p.gn_stats = None
-    p.gn_cpg = 0
+    p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    p.gn_cpg = gn_cpg if gn_stats is not None else 0
     _count()
     if _PROFILE["on"]:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -137,14 +137,33 @@ def _alloc_out(shape, planes, terms, device):
     return torch.empty(tuple(shape), dtype=torch.float32, device=device)
 
 
-def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False):
-    """3x3 stride-1 pad-1 conv.  a: planes [T,N,H,W,C]; w: packed planes
-    [T,9,Cout,C] (see pack_conv_weight); bias fp32 [Cout].  Returns fp32 NHWC
-    [N,H,W,Cout] (or NCHW with nchw_out) or planes [T,N,H,W,Cout]."""
+GN_GROUPS = 32
+
+
+def new_gn_stats(n, device):
+    """zeroed (sum, sumsq) accumulators [n, 32, 2] fp64 for a fused GroupNorm-statistics epilogue"""
+    return torch.zeros((n, GN_GROUPS, 2), dtype=torch.float64, device=device)
+
+
+def _stats_for(cout, n, device, want):
+    """GroupNorm(32) statistics can ride in the epilogue when channels-per-group is a power of two >= 2"""
+    cpg = cout // GN_GROUPS
+    if not want or cout % GN_GROUPS != 0 or cpg < 2 or (cpg & (cpg - 1)) != 0:
+        return None, 0
+    return new_gn_stats(n, device), cpg
+
+
+def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False, want_stats=False, taps=None):
+    """3x3 stride-1 pad-1 conv (or, with taps=_TAPS_1 and a [T,1,Cout,C] weight, a 1x1 conv).
+    a: planes [T,N,H,W,C]; w: packed planes [T,ntaps,Cout,C] (see pack_conv_weight); bias fp32 [Cout].
+    Returns fp32 NHWC [N,H,W,Cout] (or NCHW with nchw_out) or planes [T,N,H,W,Cout]; with
+    want_stats also the fused GroupNorm statistics of the fp32 output (or None if not applicable)."""
     _need_cuda(a, w)
     T, N, H, W, Cc = a.shape
     Cout = w.shape[2]
-    assert w.shape[1] == 9 and w.shape[3] == Cc, (a.shape, w.shape)
+    taps = taps if taps is not None else _TAPS_3x3
+    assert w.shape[1] == len(taps) and w.shape[3] == Cc, (a.shape, w.shape)
+    stats, cpg = _stats_for(Cout, N, a.device, want_stats and not planes_out and not nchw_out)
     if nchw_out:
         out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=a.device)
         d_strides = (Cout * H * W, W, 1, H * W)
@@ -153,13 +172,23 @@ def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False):
         d_strides = (H * W * Cout, W * Cout, Cout, 1)
     _tapgemm(a=a, a_term_imgs=N, a_imgs=T * N, a_bcast=0, n_img=N, H=H, W=W, a_H=H, a_W=W, Cc=Cc,
              a_sw=Cc, a_sh=W * Cc, a_sn=H * W * Cc,
-             b=w, b_term_g=9, b_groups=w.shape[0] * 9, b_batched=0, n_out=Cout, b_sn=Cc, b_sg=Cout * Cc,
-             taps=_TAPS_3x3, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
-             d_plane=N * H * W * Cout, bias=bias, bias_mode=BIAS_COL, residual=residual)
+             b=w, b_term_g=len(taps), b_groups=w.shape[0] * len(taps), b_batched=0, n_out=Cout, b_sn=Cc,
+             b_sg=Cout * Cc,
+             taps=taps, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
+             d_plane=N * H * W * Cout, bias=bias, bias_mode=BIAS_COL, residual=residual,
+             gn_stats=stats, gn_cpg=cpg)
+    if want_stats:
+        return out, stats
     return out
 
 
-def conv3x3_s2(a_ph, w, bias):
+def conv1x1(a, w, bias, *, residual=None, planes_out=False, want_stats=False):
+    """1x1 conv on planes [T,N,H,W,C] with a pack_linear_weight()-packed weight [T,1,Cout,C]; tiles stay
+    inside one image so GroupNorm statistics can be fused."""
+    return conv3x3(a, w, bias, residual=residual, planes_out=planes_out, want_stats=want_stats, taps=_TAPS_1)
+
+
+def conv3x3_s2(a_ph, w, bias, *, want_stats=False):
     """Downsample conv: pad (0,1,0,1) then 3x3 stride 2 (vqgan_arch.py:547-551).
     a_ph: space-to-depth planes [T,4,N,Ho,Wo,C] from f32_to_planes(mode=S2D)."""
     _need_cuda(a_ph, w)
@@ -167,12 +196,15 @@ def conv3x3_s2(a_ph, w, bias):
     assert four == 4
     Cout = w.shape[2]
     out = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=a_ph.device)
+    stats, cpg = _stats_for(Cout, N, a_ph.device, want_stats)
     taps = tuple((kh // 2, kw // 2, ((kh % 2) * 2 + (kw % 2)) * N) for kh in range(3) for kw in range(3))
     _tapgemm(a=a_ph, a_term_imgs=4 * N, a_imgs=T * 4 * N, a_bcast=0, n_img=N, H=Ho, W=Wo, a_H=Ho, a_W=Wo,
              Cc=Cc, a_sw=Cc, a_sh=Wo * Cc, a_sn=Ho * Wo * Cc,
              b=w, b_term_g=9, b_groups=w.shape[0] * 9, b_batched=0, n_out=Cout, b_sn=Cc, b_sg=Cout * Cc,
              taps=taps, d=out, d_mode=OUT_F32, d_strides=(Ho * Wo * Cout, Wo * Cout, Cout, 1),
-             bias=bias, bias_mode=BIAS_COL)
+             bias=bias, bias_mode=BIAS_COL, gn_stats=stats, gn_cpg=cpg)
+    if want_stats:
+        return out, stats
     return out
 
 
@@ -342,15 +374,18 @@ def f32_to_planes(x, mode=CVT_PLAIN, terms=None):
     return out
 
 
-def group_norm(x, gamma, beta, *, swish, groups=32, eps=1e-6, terms=None):
-    """GroupNorm(32, C, eps=1e-6) (+ swish) of fp32 NHWC x -> planes [T,N,H,W,C]."""
+def group_norm(x, gamma, beta, *, swish, groups=32, eps=1e-6, terms=None, stats=None):
+    """GroupNorm(32, C, eps=1e-6) (+ swish) of fp32 NHWC x -> planes [T,N,H,W,C].
+    ``stats``: (sum, sumsq) [N,groups,2] fp64 already accumulated by the producer's epilogue."""
     _need_cuda(x)
     N, H, W, Cc = x.shape
     terms = terms or get_terms()
     lib = _lib.load()
-    stats = torch.zeros((N, groups, 2), dtype=torch.float64, device=x.device)
-    _count(2)
-    _lib.check(lib.t2h_gn_stats(_ptr(x), _ptr(stats), N, H * W, Cc, groups, _stream()))
+    _count(1)
+    if stats is None:
+        stats = torch.zeros((N, groups, 2), dtype=torch.float64, device=x.device)
+        _count(1)
+        _lib.check(lib.t2h_gn_stats(_ptr(x), _ptr(stats), N, H * W, Cc, groups, _stream()))
     out = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device)
     _lib.check(lib.t2h_gn_apply(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), N, H * W, Cc,
                                 groups, eps, 1 if swish else 0, terms, _stream()))

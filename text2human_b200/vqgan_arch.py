@@ -57,14 +57,21 @@ def _f32(p):
     return p.detach()
 
 
-def conv1x1_nhwc(x, conv, *, residual=None, planes_in=None):
-    """1x1 conv on fp32 NHWC ``x`` (or on planes ``planes_in``) -> fp32 NHWC."""
+class _Act:
+    """fp32 NHWC activation + (optionally) the GroupNorm(32) statistics of it that the producing
+    kernel's epilogue accumulated, so the consumer's GroupNorm skips its statistics pass."""
+    __slots__ = ("x", "stats")
+
+    def __init__(self, x, stats=None):
+        self.x = x
+        self.stats = stats
+
+
+def conv1x1_nhwc(x, conv, *, residual=None, planes_in=None, want_stats=False):
+    """1x1 conv on fp32 NHWC ``x`` (or on planes ``planes_in``) -> fp32 NHWC (and its GN statistics)."""
     if planes_in is None:
         planes_in = ops.f32_to_planes(x, CVT_PLAIN)
-    T, N, H, W, Cc = planes_in.shape
-    res2d = residual.reshape(N * H * W, -1) if residual is not None else None
-    out = ops.linear(planes_in.reshape(T, N * H * W, Cc), _lin_w(conv), _f32(conv.bias), residual=res2d)
-    return out.view(N, H, W, -1)
+    return ops.conv1x1(planes_in, _lin_w(conv), _f32(conv.bias), residual=residual, want_stats=want_stats)
 
 
 # ----------------------------------------------------------------------------
@@ -74,9 +81,10 @@ def Normalize(in_channels):
     return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
 
 
-def _gn(x, norm, swish):
-    return ops.group_norm(x, _f32(norm.weight), _f32(norm.bias), swish=swish, groups=norm.num_groups,
-                          eps=norm.eps)
+def _gn(act, norm, swish):
+    stats = act.stats if norm.num_groups == ops.GN_GROUPS else None
+    return ops.group_norm(act.x, _f32(norm.weight), _f32(norm.bias), swish=swish, groups=norm.num_groups,
+                          eps=norm.eps, stats=stats)
 
 
 class Upsample(nn.Module):
@@ -88,11 +96,14 @@ class Upsample(nn.Module):
         if self.with_conv:
             self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
 
-    def forward_nhwc(self, x):
+    def _fwd(self, act):
         if not self.with_conv:
             raise NotImplementedError("Upsample(with_conv=False) is not on the Text2Human path")
-        a = ops.f32_to_planes(x, CVT_UP2X)  # the x2 replication happens in the fp16 split pass
-        return ops.conv3x3(a, _conv_w(self.conv), _f32(self.conv.bias))
+        a = ops.f32_to_planes(act.x, CVT_UP2X)  # the x2 replication happens in the fp16 split pass
+        return _Act(*ops.conv3x3(a, _conv_w(self.conv), _f32(self.conv.bias), want_stats=True))
+
+    def forward_nhwc(self, x):
+        return self._fwd(_Act(x)).x
 
     def forward(self, x):
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x)))
@@ -107,11 +118,14 @@ class Downsample(nn.Module):
         if self.with_conv:
             self.conv = torch.nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
-    def forward_nhwc(self, x):
+    def _fwd(self, act):
         if not self.with_conv:
             raise NotImplementedError("Downsample(with_conv=False) is not on the Text2Human path")
-        a = ops.f32_to_planes(x, CVT_S2D)
-        return ops.conv3x3_s2(a, _conv_w(self.conv), _f32(self.conv.bias))
+        a = ops.f32_to_planes(act.x, CVT_S2D)
+        return _Act(*ops.conv3x3_s2(a, _conv_w(self.conv), _f32(self.conv.bias), want_stats=True))
+
+    def forward_nhwc(self, x):
+        return self._fwd(_Act(x)).x
 
     def forward(self, x):
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x)))
@@ -143,11 +157,12 @@ class ResnetBlock(nn.Module):
                 self.nin_shortcut = torch.nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1,
                                                     padding=0)
 
-    def forward_nhwc(self, x, temb=None):
-        assert temb is None, "temb is always None on the Text2Human path (temb_ch=0)"
+    def _fwd(self, act):
         assert self.dropout.p == 0.0 or not self.training, "dropout>0 in training is not implemented"
-        a = _gn(x, self.norm1, swish=True)
-        h = ops.conv3x3(a, _conv_w(self.conv1), _f32(self.conv1.bias))
+        x = act.x
+        a = _gn(act, self.norm1, swish=True)
+        # conv1's epilogue accumulates the statistics norm2 needs
+        h = _Act(*ops.conv3x3(a, _conv_w(self.conv1), _f32(self.conv1.bias), want_stats=True))
         a = _gn(h, self.norm2, swish=True)
         if self.in_channels != self.out_channels:
             xp = ops.f32_to_planes(x, CVT_PLAIN)
@@ -155,8 +170,12 @@ class ResnetBlock(nn.Module):
                 x = ops.conv3x3(xp, _conv_w(self.conv_shortcut), _f32(self.conv_shortcut.bias))
             else:
                 x = conv1x1_nhwc(None, self.nin_shortcut, planes_in=xp)
-        # residual add fused into conv2's epilogue
-        return ops.conv3x3(a, _conv_w(self.conv2), _f32(self.conv2.bias), residual=x)
+        # residual add (and the next GroupNorm's statistics) fused into conv2's epilogue
+        return _Act(*ops.conv3x3(a, _conv_w(self.conv2), _f32(self.conv2.bias), residual=x, want_stats=True))
+
+    def forward_nhwc(self, x, temb=None):
+        assert temb is None, "temb is always None on the Text2Human path (temb_ch=0)"
+        return self._fwd(_Act(x)).x
 
     def forward(self, x, temb=None):
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x), temb))
@@ -182,10 +201,11 @@ class AttnBlock(nn.Module):
                     lambda: torch.cat((self.q.bias, self.k.bias), 0).float().contiguous())
         return w, b
 
-    def forward_nhwc(self, x):
+    def _fwd(self, act):
+        x = act.x
         N, H, W, Cc = x.shape
         HW = H * W
-        hn = _gn(x, self.norm, swish=False)  # planes [T,N,H,W,C]
+        hn = _gn(act, self.norm, swish=False)  # planes [T,N,H,W,C]
         T = hn.shape[0]
         wqk, bqk = self._qk_packed()
         qk = ops.linear(hn.reshape(T, N * HW, Cc), wqk, bqk, planes_out=True).view(T, N, HW, 2 * Cc)
@@ -196,9 +216,11 @@ class AttnBlock(nn.Module):
         s = ops.bmm_nt(q, k)  # fp32 [N,HW,HW], s[b,i,j] = sum_c q[b,i,c] k[b,j,c]
         p = ops.softmax_rows(s, scale=float(int(Cc) ** (-0.5)))  # planes [T,N,HW,HW]
         o = ops.bmm_nt(p, vt, planes_out=True)  # [T,N,HW,C]
-        out = ops.linear(o.view(T, N * HW, Cc), _lin_w(self.proj_out), _f32(self.proj_out.bias),
-                         residual=x.reshape(N * HW, Cc))
-        return out.view(N, H, W, Cc)
+        return _Act(*ops.conv1x1(o.view(T, N, H, W, Cc), _lin_w(self.proj_out), _f32(self.proj_out.bias),
+                                 residual=x, want_stats=True))
+
+    def forward_nhwc(self, x):
+        return self._fwd(_Act(x)).x
 
     def forward(self, x):
         return ops.nhwc_to_nchw(self.forward_nhwc(ops.nchw_to_nhwc(x)))
@@ -210,16 +232,16 @@ class AttnBlock(nn.Module):
 def _conv_in_nchw(conv, x):
     """network-entry conv: fp32 NCHW -> (split + NHWC + channel pad) -> 3x3 conv -> fp32 NHWC"""
     a = ops.nchw_to_planes(x)
-    return ops.conv3x3(a, _conv_w(conv, a.shape[-1]), _f32(conv.bias))
+    return _Act(*ops.conv3x3(a, _conv_w(conv, a.shape[-1]), _f32(conv.bias), want_stats=True))
 
 
 def _conv_in_nhwc(conv, x):
     a = ops.f32_to_planes(x, CVT_PLAIN)
-    return ops.conv3x3(a, _conv_w(conv), _f32(conv.bias))
+    return _Act(*ops.conv3x3(a, _conv_w(conv), _f32(conv.bias), want_stats=True))
 
 
-def _conv_out(norm, conv, h, nchw):
-    a = _gn(h, norm, swish=True)
+def _conv_out(norm, conv, act, nchw):
+    a = _gn(act, norm, swish=True)
     return ops.conv3x3(a, _conv_w(conv), _f32(conv.bias), nchw_out=nchw)
 
 
@@ -274,14 +296,14 @@ class Encoder(nn.Module):
         for i_level in range(self.num_resolutions):
             lvl = self.down[i_level]
             for i_block in range(self.num_res_blocks):
-                h = lvl.block[i_block].forward_nhwc(h)
+                h = lvl.block[i_block]._fwd(h)
                 if len(lvl.attn) > 0:
-                    h = lvl.attn[i_block].forward_nhwc(h)
+                    h = lvl.attn[i_block]._fwd(h)
             if i_level != self.num_resolutions - 1:
-                h = lvl.downsample.forward_nhwc(h)
-        h = self.mid.block_1.forward_nhwc(h)
-        h = self.mid.attn_1.forward_nhwc(h)
-        h = self.mid.block_2.forward_nhwc(h)
+                h = lvl.downsample._fwd(h)
+        h = self.mid.block_1._fwd(h)
+        h = self.mid.attn_1._fwd(h)
+        h = self.mid.block_2._fwd(h)
         return h
 
     @torch.no_grad()
@@ -346,29 +368,29 @@ class Decoder(nn.Module):
         self.conv_out = torch.nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
 
     def _trunk(self, h, bot_h=None, stop_after_level=None, mid_h=None):
-        h = self.mid.block_1.forward_nhwc(h)
-        h = self.mid.attn_1.forward_nhwc(h)
-        h = self.mid.block_2.forward_nhwc(h)
+        h = self.mid.block_1._fwd(h)
+        h = self.mid.attn_1._fwd(h)
+        h = self.mid.block_2._fwd(h)
         for i_level in reversed(range(self.num_resolutions)):
             lvl = self.up[i_level]
             for i_block in range(self.num_res_blocks + 1):
-                h = lvl.block[i_block].forward_nhwc(h)
+                h = lvl.block[i_block]._fwd(h)
                 if len(lvl.attn) > 0:
-                    h = lvl.attn[i_block].forward_nhwc(h)
+                    h = lvl.attn[i_block]._fwd(h)
             if i_level != 0:
-                h = lvl.upsample.forward_nhwc(h)
+                h = lvl.upsample._fwd(h)
             # reference :1023-1024 — the hierarchy residual enters after level 4's upsample
             if i_level == 4 and bot_h is not None:
-                ops.add_inplace(h, bot_h)
+                h = _Act(ops.add_inplace(h.x, bot_h))  # statistics of the sum are not known
             if i_level == 4 and mid_h is not None:
-                ops.add_inplace(h, mid_h)
+                h = _Act(ops.add_inplace(h.x, mid_h))
             if stop_after_level is not None and i_level == stop_after_level:
                 return h
         return h
 
     def _finish(self, h, nchw):
         if self.give_pre_end:
-            return ops.nhwc_to_nchw(h) if nchw else h
+            return ops.nhwc_to_nchw(h.x) if nchw else h.x
         return _conv_out(self.norm_out, self.conv_out, h, nchw=nchw)
 
     @torch.no_grad()
@@ -390,14 +412,14 @@ class Decoder(nn.Module):
         """reference :1035-1059 — activations after level 4's upsample"""
         self.last_z_shape = z.shape
         h = self._trunk(_conv_in_nchw(self.conv_in, z), stop_after_level=4)
-        return ops.nhwc_to_nchw(h)
+        return ops.nhwc_to_nchw(h.x)
 
     @torch.no_grad()
     def get_feature_middle(self, z, mid_h):
         """reference :1061-1087 — adds mid_h after level 4, returns after level 3"""
         self.last_z_shape = z.shape
         h = self._trunk(_conv_in_nchw(self.conv_in, z), mid_h=ops.nchw_to_nhwc(mid_h), stop_after_level=3)
-        return ops.nhwc_to_nchw(h)
+        return ops.nhwc_to_nchw(h.x)
 
 
 class DecoderRes(nn.Module):
@@ -427,9 +449,9 @@ class DecoderRes(nn.Module):
                                        temb_channels=self.temb_ch, dropout=dropout)
 
     def _trunk(self, h):
-        h = self.mid.block_1.forward_nhwc(h)
-        h = self.mid.attn_1.forward_nhwc(h)
-        return self.mid.block_2.forward_nhwc(h)
+        h = self.mid.block_1._fwd(h)
+        h = self.mid.attn_1._fwd(h)
+        return self.mid.block_2._fwd(h).x
 
     @torch.no_grad()
     def forward_nhwc(self, z):
