@@ -1,18 +1,21 @@
 // t2h_tapgemm: persistent, warp-specialised tcgen05 implicit-GEMM for sm_100a.
 //
-//   warp 0   TMA producer   cp.async.bulk.tensor (4-D activation boxes with
-//                           zero OOB fill = conv padding; 4-D weight boxes)
-//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16),
-//                           accumulators live in tensor memory, double-buffered
+//   warp 0   A producer     cp.async.bulk.tensor 4-D activation "slabs": the rows a tile needs
+//                           for all vertical taps of one horizontal shift (zero OOB fill =
+//                           conv padding), so a 3x3 conv loads activations 3x, not 9x
+//   warp 3   B producer     4-D weight boxes, one per tap (own ring: no head-of-line blocking)
+//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) on shifted views
+//                           of the slab; accumulators live in tensor memory, double-buffered
 //   warp 2   TMEM allocator
 //   warps 4-7 epilogue      tcgen05.ld -> alpha/bias/GELU/residual/GroupNorm
 //                           partial sums -> swizzled smem staging -> TMA store
 //                           (residual tiles arrive by TMA load into smem)
 //
-// The contraction loop runs over (tap, 64-channel chunk, product term).  A tap
-// is a spatial shift of the activation box (3x3 conv = 9 taps, 1x1/Linear/bmm
-// = 1 tap); a product term selects which fp16 planes feed the MMA so that
-// hi*hi + hi*lo + lo*hi reproduces an fp32 product on the fp16 tensor pipe.
+// The contraction loop runs over (tap group, 64-channel chunk, tap, product term).  A tap is a
+// spatial shift of the activation box (3x3 conv = 9 taps, 1x1/Linear/bmm = 1 tap); taps with the
+// same horizontal shift form a group and share one slab.  A product term selects which fp16
+// planes feed the MMA so that hi*lo + hi*hi + lo*hi reproduces an fp32 product on the fp16 tensor
+// pipe; the hi/lo slabs and weight tiles are each loaded once per (group, chunk[, tap]).
 //
 // Replaces cuDNN/cuBLAS calls made by the reference modules — see include/t2h.h.
 #include <cuda.h>
@@ -30,8 +33,11 @@ struct TapGemmDev {
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int n_out, C, kchunks, nterms;
   int a_term_imgs, a_bcast, b_term_g, b_batched, b_batched_h;
-  int ntaps;
-  int tap_dy[T2H_MAX_TAPS], tap_dx[T2H_MAX_TAPS], tap_img_off[T2H_MAX_TAPS];
+  // taps grouped by (dx, img_off): one activation slab per group
+  int ngroups, slab_rows;
+  int a_slots, b_slots;  // ring depths (A slabs / B tiles)
+  int g_dx[T2H_MAX_TAPS], g_ioff[T2H_MAX_TAPS], g_dy0[T2H_MAX_TAPS], g_ntaps[T2H_MAX_TAPS];
+  int g_dyrel[T2H_MAX_TAPS][3], g_btap[T2H_MAX_TAPS][3];
   void* d;
   int d_mode, d_terms, epi_mode, d_term_imgs;
   long long d_plane, d_sn, d_sh, d_sw, d_sc;
@@ -49,20 +55,18 @@ constexpr int kThreads = 256;
 constexpr int kEpiBufBytes = 128 * 128;      // one staging tile: 128 rows x 128 bytes
 constexpr int kEpiBytes = 4 * kEpiBufBytes;  // 2 output + 2 residual staging tiles
 
+constexpr int kMaxSlots = 8;
+constexpr int kDynSmem = 227 * 1024 - 4096;  // opt-in limit minus ~4 KB of static shared memory
+constexpr int kRingBytes = kDynSmem - 1024 - kEpiBytes;  // A ring + B ring
+
 template <int BN, int MBLK>
 struct Cfg {
-  static constexpr int kStageBytes = MBLK * kABlockBytes + BN * 128;
-  // 227 KB opt-in limit minus alignment slack, epilogue staging and ~3 KB of static shared memory
-  static constexpr int kBudget = 227 * 1024 - 1024 - kEpiBytes - 4096;
-  static constexpr int kStagesRaw = kBudget / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  // A ring: slabs of (MBLK*TH + 2) x TW positions x 128 bytes (TW <= 16 whenever taps share a slab)
+  static constexpr int kASlot = MBLK * kABlockBytes + 4096;
+  static constexpr int kBSlot = BN * 128;
   static constexpr int kAccCols = MBLK * BN;
   static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : (2 * kAccCols);
   static constexpr int kChunk = BN < 32 ? BN : 32;  // columns per tcgen05.ld in the direct epilogue
-  // >= 120 KB so that at most one CTA (and one TMEM allocation) lives on an SM
-  static constexpr int kSmemRaw = kStages * kStageBytes + kEpiBytes + 1024;
-  static constexpr int kSmemBytes = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
-  static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kTmemCols <= 512, "accumulators exceed tensor memory");
   static_assert((kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be a power of two");
 };
@@ -136,15 +140,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ TapGemmDev P) {
   using C = Cfg<BN, MBLK>;
-  constexpr int STAGES = C::kStages;
+  const int NA = P.a_slots, NB = P.b_slots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_buf = smem + STAGES * C::kStageBytes;  // 2 tiles
-  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;      // 2 tiles
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + NA * C::kASlot;
+  uint8_t* out_buf = b_ring + NB * C::kBSlot;     // 2 tiles
+  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;  // 2 tiles
 
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t a_full[kMaxSlots];
+  __shared__ __align__(8) uint64_t a_empty[kMaxSlots];
+  __shared__ __align__(8) uint64_t b_full[kMaxSlots];
+  __shared__ __align__(8) uint64_t b_empty[kMaxSlots];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t res_bar[2];
@@ -161,9 +169,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (P.epi_mode == EPI_TMA_F32 && P.residual) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -182,35 +194,53 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  const int kiters = P.ntaps * P.kchunks * P.nterms;
+  const int a_planes = (P.nterms == 3) ? 2 : 1;  // slabs per (group, chunk): hi [, lo]
+  const int slab_bytes = P.slab_rows * P.TW * 128;
 
   if (warp == 0) {
-    // ------------------------------------------------------- TMA producer
+    // ---------------------------------------------- A producer (activation slabs)
     if (lane == 0) {
-      int stage = 0, phase = 0;
+      int sa = 0, pa = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, MBLK, BN);
         const int a_img = P.a_bcast ? 0 : t.img;
+        for (int g = 0; g < P.ngroups; ++g) {
+          for (int ch = 0; ch < P.kchunks; ++ch) {
+            for (int pl = 0; pl < a_planes; ++pl) {  // hi, then lo
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              mbar_expect_tx(&a_full[sa], slab_bytes);
+              tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
+                          t.h0 + P.g_dy0[g], a_img + P.g_ioff[g] + pl * P.a_term_imgs);
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------- B producer (weight tiles)
+    if (lane == 0) {
+      int sb = 0, pb = 0;
+      const int b_planes = a_planes;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile, MBLK, BN);
         const int b_g2 = P.b_batched ? t.img : 0;
         const int b_g = P.b_batched_h ? t.h0 : 0;
-        for (int tap = 0; tap < P.ntaps; ++tap) {
-          const int dy = P.tap_dy[tap], dx = P.tap_dx[tap], ioff = P.tap_img_off[tap];
+        for (int g = 0; g < P.ngroups; ++g) {
           for (int ch = 0; ch < P.kchunks; ++ch) {
-            for (int term = 0; term < P.nterms; ++term) {
-              const int ta = (term == 2) ? P.a_term_imgs : 0;  // lo plane of A
-              const int tb = (term == 1) ? P.b_term_g : 0;     // lo plane of B
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-              uint8_t* sa = smem + stage * C::kStageBytes;
-#pragma unroll
-              for (int mb = 0; mb < MBLK; ++mb)
-                tma_load_4d(&tmA, &full_bar[stage], sa + mb * kABlockBytes, ch * kBK, t.w0 + dx,
-                            t.h0 + mb * P.TH + dy, a_img + ioff + ta);
-              tma_load_4d(&tmB, &full_bar[stage], sa + MBLK * kABlockBytes, ch * kBK, t.n0,
-                          b_g + tap + tb, b_g2);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
+            for (int tp = 0; tp < P.g_ntaps[g]; ++tp) {
+              for (int pl = b_planes - 1; pl >= 0; --pl) {  // lo first, then hi (consumption order)
+                mbar_wait(&b_empty[sb], pb ^ 1);
+                mbar_expect_tx(&b_full[sb], C::kBSlot);
+                tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
+                            b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                if (++sb == NB) {
+                  sb = 0;
+                  pb ^= 1;
+                }
               }
             }
           }
@@ -222,30 +252,79 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t IDESC = umma_idesc_f16(128, BN);
       const int last_steps = (P.C - (P.kchunks - 1) * kBK + 15) / 16;  // UMMA_K=16 steps
-      int stage = 0, phase = 0, as = 0, ap = 0;
+      const int row_bytes = P.TW * 128;  // one image row of the slab
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], ap ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * C::kAccCols;
-        for (int it = 0; it < kiters; ++it) {
-          const int ch = (it / P.nterms) % P.kchunks;
-          const int ksteps = (ch == P.kchunks - 1) ? last_steps : 4;
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + MBLK * kABlockBytes;
+        bool fresh = true;  // first MMA of the tile overwrites the accumulator
+        // D (+)= A_view(dyrel) * B_tile
+        auto mma_batch = [&](uint32_t a_addr, uint32_t b_addr, int dyrel, int ksteps) {
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t bdesc = umma_desc_k128(b_addr + j * 32);
 #pragma unroll
             for (int mb = 0; mb < MBLK; ++mb) {
-              const uint64_t adesc = umma_desc_k128(a_addr + mb * kABlockBytes + j * 32);
-              umma_f16(d_base + mb * BN, adesc, bdesc, IDESC, (it > 0 || j > 0) ? 1u : 0u);
+              const uint64_t adesc =
+                  umma_desc_k128(a_addr + (mb * P.TH + dyrel) * row_bytes + j * 32);
+              umma_f16(d_base + mb * BN, adesc, bdesc, IDESC, (fresh && j == 0) ? 0u : 1u);
             }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          fresh = false;
+        };
+        auto adv_b = [&]() {
+          if (++sb == NB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        };
+        for (int g = 0; g < P.ngroups; ++g) {
+          const int nt = P.g_ntaps[g];
+          for (int ch = 0; ch < P.kchunks; ++ch) {
+            const int ksteps = (ch == P.kchunks - 1) ? last_steps : 4;
+            // slab slots of this (group, chunk)
+            const int sa_hi = sa;
+            const int pa_hi = pa;
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+            int sa_lo = sa, pa_lo = pa;
+            if (a_planes == 2) {
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+            mbar_wait(&a_full[sa_hi], pa_hi);
+            tc_fence_after();
+            const uint32_t ahi = smem_u32(a_ring + sa_hi * C::kASlot);
+            const uint32_t alo = smem_u32(a_ring + sa_lo * C::kASlot);
+            for (int tp = 0; tp < nt; ++tp) {
+              const int dyrel = P.g_dyrel[g][tp];
+              if (a_planes == 1) {
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                mma_batch(ahi, smem_u32(b_ring + sb * C::kBSlot), dyrel, ksteps);
+                umma_commit(&b_empty[sb]);
+                adv_b();
+              } else {
+                // hi*lo
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                mma_batch(ahi, smem_u32(b_ring + sb * C::kBSlot), dyrel, ksteps);
+                umma_commit(&b_empty[sb]);
+                adv_b();
+                // hi*hi, then lo*hi on the same weight tile
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                const uint32_t bhi = smem_u32(b_ring + sb * C::kBSlot);
+                mma_batch(ahi, bhi, dyrel, ksteps);
+                if (tp == nt - 1) umma_commit(&a_empty[sa_hi]);  // hi slab done
+                if (tp == 0) {
+                  mbar_wait(&a_full[sa_lo], pa_lo);
+                  tc_fence_after();
+                }
+                mma_batch(alo, bhi, dyrel, ksteps);
+                umma_commit(&b_empty[sb]);
+                adv_b();
+              }
+            }
+            umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]);
           }
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete
@@ -579,11 +658,19 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   static bool configured = false;
   if (!configured) {
     T2H_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN, MBLK>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
     configured = true;
   }
+  // ring depths: enough bytes in flight to cover the TMA round trip at the tile's consumption rate.
+  // With the 3-product split both (hi, lo) slabs of a (group, chunk) are live at once.
+  TapGemmDev Q = P;
+  Q.a_slots = (MBLK == 2 || BN == 256) ? 3 : 4;
+  int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
+  Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
+  if (Q.b_slots < 3) return fail(T2H_EINVAL, "tapgemm: shared-memory rings do not fit");
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  tapgemm_kernel<BN, MBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmD, tmR, P);
+  // the full dynamic allocation also keeps it to one CTA (one TMEM allocation) per SM
+  tapgemm_kernel<BN, MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -614,12 +701,6 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   P.n_out = p->n_out; P.C = p->C; P.kchunks = (p->C + kBK - 1) / kBK; P.nterms = p->nterms;
   P.a_term_imgs = p->a_term_imgs; P.a_bcast = p->a_bcast;
   P.b_term_g = p->b_term_g; P.b_batched = p->b_batched; P.b_batched_h = p->b_batched_h;
-  P.ntaps = p->ntaps;
-  for (int i = 0; i < T2H_MAX_TAPS; ++i) {
-    P.tap_dy[i] = i < p->ntaps ? p->tap_dy[i] : 0;
-    P.tap_dx[i] = i < p->ntaps ? p->tap_dx[i] : 0;
-    P.tap_img_off[i] = i < p->ntaps ? p->tap_img_off[i] : 0;
-  }
   P.d = p->d; P.d_mode = p->d_mode; P.d_terms = p->d_terms; P.d_plane = p->d_plane;
   P.d_sn = p->d_sn; P.d_sh = p->d_sh; P.d_sw = p->d_sw; P.d_sc = p->d_sc;
   P.bias = p->bias; P.bias_mode = p->bias_mode; P.act = p->act; P.alpha = p->alpha;
@@ -645,6 +726,42 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     if (tiles1 >= 4LL * num_sms()) MBLK = 2;
   }
   P.TW = TW; P.TH = TH;
+  // ---- tap groups: taps with the same (dx, img_off) share one activation slab when a vertical
+  // shift of the slab view stays 1024-byte aligned (TW*128 bytes per image row, TW >= 8)
+  {
+    const bool can_share = (TW >= 8) && (TW <= 16);
+    P.ngroups = 0;
+    int gmin[T2H_MAX_TAPS], gmax[T2H_MAX_TAPS];
+    int gt_dy[T2H_MAX_TAPS][3];
+    for (int i = 0; i < p->ntaps; ++i) {
+      int g = -1;
+      if (can_share)
+        for (int k = 0; k < P.ngroups; ++k)
+          if (P.g_dx[k] == p->tap_dx[i] && P.g_ioff[k] == p->tap_img_off[i] && P.g_ntaps[k] < 3) {
+            const int lo = p->tap_dy[i] < gmin[k] ? p->tap_dy[i] : gmin[k];
+            const int hi = p->tap_dy[i] > gmax[k] ? p->tap_dy[i] : gmax[k];
+            if (hi - lo <= 2) { g = k; gmin[k] = lo; gmax[k] = hi; break; }
+          }
+      if (g < 0) {
+        g = P.ngroups++;
+        P.g_dx[g] = p->tap_dx[i]; P.g_ioff[g] = p->tap_img_off[i]; P.g_ntaps[g] = 0;
+        gmin[g] = gmax[g] = p->tap_dy[i];
+      }
+      gt_dy[g][P.g_ntaps[g]] = p->tap_dy[i];
+      P.g_btap[g][P.g_ntaps[g]] = i;
+      P.g_ntaps[g]++;
+    }
+    int extra = 0;
+    for (int g = 0; g < P.ngroups; ++g) {
+      P.g_dy0[g] = gmin[g];
+      for (int k = 0; k < P.g_ntaps[g]; ++k) P.g_dyrel[g][k] = gt_dy[g][k] - gmin[g];
+      if (gmax[g] - gmin[g] > extra) extra = gmax[g] - gmin[g];
+    }
+    for (int g = P.ngroups; g < T2H_MAX_TAPS; ++g) {
+      P.g_dx[g] = P.g_ioff[g] = P.g_dy0[g] = P.g_ntaps[g] = 0;
+    }
+    P.slab_rows = MBLK * TH + extra;
+  }
   P.tiles_w = ceil_div(p->W, TW);
   P.tiles_h = ceil_div(p->H, TH * MBLK);
   P.n_tiles_n = ceil_div(p->n_out, BN);
@@ -681,7 +798,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   {
     uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->a_W, (uint64_t)p->a_H, (uint64_t)p->a_imgs};
     uint64_t str[4] = {1, (uint64_t)p->a_sw, (uint64_t)p->a_sh, (uint64_t)p->a_sn};
-    uint32_t box[4] = {(uint32_t)kBK, (uint32_t)TW, (uint32_t)TH, 1};
+    uint32_t box[4] = {(uint32_t)kBK, (uint32_t)TW, (uint32_t)P.slab_rows, 1};
     int rc = make_tmap(&tmA, p->a, 2, 4, dims, str, box, "tapgemm A");
     if (rc) return rc;
   }
