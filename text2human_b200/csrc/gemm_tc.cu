@@ -19,6 +19,7 @@
 //
 // Replaces cuDNN/cuBLAS calls made by the reference modules — see include/t2h.h.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "t2h_internal.h"
 #include "t2h_ptx.cuh"
@@ -36,6 +37,8 @@ struct TapGemmDev {
   // taps grouped by (dx, img_off): one activation slab per group
   int ngroups, slab_rows;
   int a_slots, b_slots;  // ring depths (A slabs / B tiles)
+  int debug;             // T2H_DEBUG bits (profiling experiments only): 1 skip epilogue work,
+                         // 2 skip MMA issue, 4 skip TMA loads
   int g_dx[T2H_MAX_TAPS], g_ioff[T2H_MAX_TAPS], g_dy0[T2H_MAX_TAPS], g_ntaps[T2H_MAX_TAPS];
   int g_dyrel[T2H_MAX_TAPS][3], g_btap[T2H_MAX_TAPS][3];
   void* d;
@@ -208,9 +211,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int ch = 0; ch < P.kchunks; ++ch) {
             for (int pl = 0; pl < a_planes; ++pl) {  // hi, then lo
               mbar_wait(&a_empty[sa], pa ^ 1);
-              mbar_expect_tx(&a_full[sa], slab_bytes);
-              tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
-                          t.h0 + P.g_dy0[g], a_img + P.g_ioff[g] + pl * P.a_term_imgs);
+              if (P.debug & 4) {
+                mbar_arrive(&a_full[sa]);
+              } else {
+                mbar_expect_tx(&a_full[sa], slab_bytes);
+                tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
+                            t.h0 + P.g_dy0[g], a_img + P.g_ioff[g] + pl * P.a_term_imgs);
+              }
               if (++sa == NA) {
                 sa = 0;
                 pa ^= 1;
@@ -234,9 +241,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int tp = 0; tp < P.g_ntaps[g]; ++tp) {
               for (int pl = b_planes - 1; pl >= 0; --pl) {  // lo first, then hi (consumption order)
                 mbar_wait(&b_empty[sb], pb ^ 1);
-                mbar_expect_tx(&b_full[sb], C::kBSlot);
-                tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
-                            b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                if (P.debug & 4) {
+                  mbar_arrive(&b_full[sb]);
+                } else {
+                  mbar_expect_tx(&b_full[sb], C::kBSlot);
+                  tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
+                              b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                }
                 if (++sb == NB) {
                   sb = 0;
                   pb ^= 1;
@@ -261,6 +272,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bool fresh = true;  // first MMA of the tile overwrites the accumulator
         // D (+)= A_view(dyrel) * B_tile
         auto mma_batch = [&](uint32_t a_addr, uint32_t b_addr, int dyrel, int ksteps) {
+          if (P.debug & 2) return;
           for (int j = 0; j < ksteps; ++j) {
             const uint64_t bdesc = umma_desc_k128(b_addr + j * 32);
 #pragma unroll
@@ -380,6 +392,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          }
+          if (P.debug & 1) {
+            if (has_res) {
+              mbar_wait(&res_bar[buf], res_par[buf]);
+              res_par[buf] ^= 1;
+              named_bar_sync(2, 128);
+              if (elected && u + 2 < nunits) issue_res(u + 2, buf);
+            }
+            buf ^= 1;
+            continue;
           }
           float v[32];
           const float row_bias =
@@ -600,6 +622,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+}  // namespace t2h
+
+#include "gemm_tc_swap.cuh"
+
+namespace t2h {
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -664,6 +692,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   // ring depths: enough bytes in flight to cover the TMA round trip at the tile's consumption rate.
   // With the 3-product split both (hi, lo) slabs of a (group, chunk) are live at once.
   TapGemmDev Q = P;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("T2H_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    Q.debug = dbg;
+  }
   Q.a_slots = (MBLK == 2 || BN == 256) ? 3 : 4;
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
@@ -671,6 +707,34 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
   // the full dynamic allocation also keeps it to one CTA (one TMEM allocation) per SM
   tapgemm_kernel<BN, MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+template <int MBLK>
+static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                       const CUtensorMap& tmR, const TapGemmDev& P, cudaStream_t stream) {
+  using C = Cfg<128, MBLK>;
+  static bool configured = false;
+  if (!configured) {
+    T2H_CUDA(cudaFuncSetAttribute(tapgemm_swap_kernel<MBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kDynSmem));
+    configured = true;
+  }
+  TapGemmDev Q = P;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("T2H_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    Q.debug = dbg;
+  }
+  Q.a_slots = (MBLK == 2) ? 3 : 4;
+  int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
+  Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
+  int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  tapgemm_swap_kernel<MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -718,10 +782,31 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     while (TW > p->W && TW > 1) TW >>= 1;  // W < 16: narrower, taller boxes
     TH = 128 / TW;
   }
+  // Swapped-operand kernel (gemm_tc_swap.cuh): spatial convs with Cout % 128 == 0 and a plain fp32
+  // NHWC destination.  The pixel tile is the UMMA N operand (256 wide = full tensor rate).
+  const bool rows_mode = (p->H == 1 || p->tile_rows);
+  bool swap = !rows_mode && TW <= 16 && p->n_out % 128 == 0 && p->d_mode == T2H_OUT_F32 && p->d_sc == 1 &&
+              p->bias_mode != T2H_BIAS_ROW && !p->a_bcast && !p->b_batched && !p->b_batched_h &&
+              p->d_sw % 4 == 0 && p->d_sh % 4 == 0 && p->d_sh > 0 && (p->n_img == 1 || (p->d_sn % 4 == 0 && p->d_sn > 0)) &&
+              reinterpret_cast<uintptr_t>(p->d) % 16 == 0 &&
+              (!p->residual || reinterpret_cast<uintptr_t>(p->residual) % 16 == 0) &&
+              (!p->gn_stats || (p->gn_cpg >= 1 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0));
+  {
+    static int no_swap = -1;
+    if (no_swap < 0) {
+      const char* e = getenv("T2H_NO_SWAP");
+      no_swap = e ? atoi(e) : 0;
+    }
+    if (no_swap) swap = false;
+  }
   int BN = 16;
   while (BN < p->n_out && BN < 256) BN <<= 1;
   int MBLK = 1;
-  if (BN == 128 && p->H >= 2 * TH && !p->tile_rows) {
+  if (swap) {
+    BN = 128;
+    const long long tiles2 = (long long)p->n_img * ceil_div(p->H, 2 * TH) * ceil_div(p->W, TW) * (p->n_out / 128);
+    MBLK = (p->H >= 2 * TH && tiles2 >= 48) ? 2 : 1;
+  } else if (BN == 128 && p->H >= 2 * TH && !p->tile_rows) {
     long long tiles1 = (long long)p->n_img * ceil_div(p->H, TH) * ceil_div(p->W, TW);
     if (tiles1 >= 4LL * num_sms()) MBLK = 2;
   }
@@ -786,7 +871,8 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   if (p->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->residual) % 16 == 0);
   if (p->bias_mode == T2H_BIAS_COL) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0);
   P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
-  if (p->gn_stats) {
+  if (swap) P.epi_mode = EPI_TMA_F32;
+  if (p->gn_stats && !swap) {
     T2H_CHECK_ARG(P.epi_mode == EPI_TMA_F32, "tapgemm: gn_stats needs an aligned fp32 NHWC output");
     T2H_CHECK_ARG(p->gn_cpg >= 2 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0,
                   "tapgemm: gn_cpg=%d must be a power of two >= 2 dividing n_out", p->gn_cpg);
@@ -827,6 +913,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     uint64_t dims[4] = {(uint64_t)p->n_out, (uint64_t)p->W, (uint64_t)p->H, imgs};
     uint64_t str[4] = {1, sw, sh, sn};
     uint32_t box[4] = {(uint32_t)(esz == 4 ? 32 : 64), (uint32_t)TW, (uint32_t)TH, 1};
+    if (swap) box[2] = (uint32_t)(32 / TW);  // one warp's 32 pixels
     int rc = make_tmap(&tmD, p->d, esz, 4, dims, str, box, "tapgemm D");
     if (rc) return rc;
     if (p->residual) {
@@ -837,6 +924,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   }
 
   cudaStream_t s = as_stream(stream);
+  if (swap) return MBLK == 2 ? launch_swap<2>(tmA, tmB, tmD, tmR, P, s) : launch_swap<1>(tmA, tmB, tmD, tmR, P, s);
   if (MBLK == 2) return launch<128, 2>(tmA, tmB, tmD, tmR, P, s);
   switch (BN) {
     case 16: return launch<16, 1>(tmA, tmB, tmD, tmR, P, s);

@@ -1,0 +1,330 @@
+// Transposed ("swapped-operand") variant of the tap-GEMM for spatial convolutions whose output
+// channel count is a multiple of 128.
+//
+// tcgen05.mma (kind::f16, M=128) occupies the tensor pipe ~120 cycles for any N <= 256
+// (tools/umma_bench.cu, profiles/r01_umma_issue_rate.txt): only N=256 instructions reach the
+// nominal 4096 MAC/clk/SM.  A 128-channel conv tiled as [pixels x couts] can only issue N=128.
+// Here the roles are swapped: the weight tile is the M=128 operand and the activation slab view
+// (256 consecutive slab rows = 256 output pixels) is the N=256 operand, so D^T[cout, pixel]
+// accumulates at full rate for every Cout that is a multiple of 128.
+//
+// Epilogue: TMEM lane = output channel, TMEM column = pixel.  Each of the 4 epilogue warps owns 32
+// channels = one 128-byte row segment of the NHWC output, works independently (no block barriers):
+// tcgen05.ld 32 pixels -> +bias (per lane) -> +residual (its own TMA-loaded 4 KB tile) -> GroupNorm
+// partial sums (two registers per thread) -> conflict-free transposed st.shared into a swizzled
+// [32 pixels][32 channels] tile -> its own TMA store.
+#pragma once
+
+namespace t2h {
+
+constexpr int kWarpTile = 32 * 128;  // 32 pixels x 32 fp32 channels
+
+template <int MBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                    const __grid_constant__ TapGemmDev P) {
+  using C = Cfg<128, MBLK>;
+  constexpr int NPIX = MBLK * 128;  // pixels per tile = UMMA N
+  const int NA = P.a_slots, NB = P.b_slots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem =
+      reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + NA * C::kASlot;
+  uint8_t* out_buf = b_ring + NB * C::kBSlot;     // 4 warps x 2 x 4 KB
+  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;  // 4 warps x 2 x 4 KB
+
+  __shared__ __align__(8) uint64_t a_full[kMaxSlots];
+  __shared__ __align__(8) uint64_t a_empty[kMaxSlots];
+  __shared__ __align__(8) uint64_t b_full[kMaxSlots];
+  __shared__ __align__(8) uint64_t b_empty[kMaxSlots];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t res_bar[4][2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (P.residual) tma_prefetch_desc(&tmR);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s >> 1][s & 1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_s, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int a_planes = (P.nterms == 3) ? 2 : 1;
+  const int slab_bytes = P.slab_rows * P.TW * 128;
+
+  if (warp == 0) {
+    // ---------------------------------------------- activation slab producer
+    if (lane == 0) {
+      int sa = 0, pa = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile, MBLK, 128);
+        for (int g = 0; g < P.ngroups; ++g)
+          for (int ch = 0; ch < P.kchunks; ++ch)
+            for (int pl = 0; pl < a_planes; ++pl) {
+              mbar_wait(&a_empty[sa], pa ^ 1);
+              if (P.debug & 4) {
+                mbar_arrive(&a_full[sa]);
+              } else {
+                mbar_expect_tx(&a_full[sa], slab_bytes);
+                tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
+                            t.h0 + P.g_dy0[g], t.img + P.g_ioff[g] + pl * P.a_term_imgs);
+              }
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1;
+              }
+            }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------- weight tile producer (128 couts x 64 k)
+    if (lane == 0) {
+      int sb = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile, MBLK, 128);
+        for (int g = 0; g < P.ngroups; ++g)
+          for (int ch = 0; ch < P.kchunks; ++ch)
+            for (int tp = 0; tp < P.g_ntaps[g]; ++tp)
+              for (int pl = a_planes - 1; pl >= 0; --pl) {  // lo first, then hi
+                mbar_wait(&b_empty[sb], pb ^ 1);
+                if (P.debug & 4) {
+                  mbar_arrive(&b_full[sb]);
+                } else {
+                  mbar_expect_tx(&b_full[sb], C::kBSlot);
+                  tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
+                              P.g_btap[g][tp] + pl * P.b_term_g, 0);
+                }
+                if (++sb == NB) {
+                  sb = 0;
+                  pb ^= 1;
+                }
+              }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------- MMA issuer: D^T[cout, pixel] += W * slab^T
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc_f16(128, NPIX);
+      const int last_steps = (P.C - (P.kchunks - 1) * kBK + 15) / 16;
+      const int row_bytes = P.TW * 128;
+      int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], ap ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + as * C::kAccCols;
+        bool fresh = true;
+        auto mma_batch = [&](uint32_t w_addr, uint32_t slab_addr, int dyrel, int ksteps) {
+          if (P.debug & 2) return;
+          for (int j = 0; j < ksteps; ++j) {
+            umma_f16(d_base, umma_desc_k128(w_addr + j * 32),
+                     umma_desc_k128(slab_addr + dyrel * row_bytes + j * 32), IDESC,
+                     (fresh && j == 0) ? 0u : 1u);
+          }
+          fresh = false;
+        };
+        auto adv_b = [&]() {
+          if (++sb == NB) {
+            sb = 0;
+            pb ^= 1;
+          }
+        };
+        for (int g = 0; g < P.ngroups; ++g) {
+          const int nt = P.g_ntaps[g];
+          for (int ch = 0; ch < P.kchunks; ++ch) {
+            const int ksteps = (ch == P.kchunks - 1) ? last_steps : 4;
+            const int sa_hi = sa, pa_hi = pa;
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+            const int sa_lo = sa, pa_lo = pa;
+            if (a_planes == 2) {
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+            mbar_wait(&a_full[sa_hi], pa_hi);
+            tc_fence_after();
+            const uint32_t ahi = smem_u32(a_ring + sa_hi * C::kASlot);
+            const uint32_t alo = smem_u32(a_ring + sa_lo * C::kASlot);
+            for (int tp = 0; tp < nt; ++tp) {
+              const int dyrel = P.g_dyrel[g][tp];
+              if (a_planes == 1) {
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                mma_batch(smem_u32(b_ring + sb * C::kBSlot), ahi, dyrel, ksteps);
+                umma_commit(&b_empty[sb]);
+                adv_b();
+              } else {
+                mbar_wait(&b_full[sb], pb);  // w_lo
+                tc_fence_after();
+                mma_batch(smem_u32(b_ring + sb * C::kBSlot), ahi, dyrel, ksteps);  // x_hi * w_lo
+                umma_commit(&b_empty[sb]);
+                adv_b();
+                mbar_wait(&b_full[sb], pb);  // w_hi
+                tc_fence_after();
+                const uint32_t whi = smem_u32(b_ring + sb * C::kBSlot);
+                mma_batch(whi, ahi, dyrel, ksteps);  // x_hi * w_hi
+                if (tp == nt - 1) umma_commit(&a_empty[sa_hi]);
+                if (tp == 0) {
+                  mbar_wait(&a_full[sa_lo], pa_lo);
+                  tc_fence_after();
+                }
+                mma_batch(whi, alo, dyrel, ksteps);  // x_lo * w_hi
+                umma_commit(&b_empty[sb]);
+                adv_b();
+              }
+            }
+            umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]);
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          ap ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------- per-warp transposed epilogue
+    const int q = warp & 3;
+    uint8_t* my_out = out_buf + q * 2 * kWarpTile;
+    uint8_t* my_res = res_buf + q * 2 * kWarpTile;
+    const bool has_res = P.residual != nullptr;
+    const int tw_shift = 31 - __clz(P.TW);    // TW is a power of two <= 32
+    const int rows_per_chunk = 32 >> tw_shift;  // image rows covered by 32 pixels
+    constexpr int NCH = NPIX / 32;
+    int as = 0, ap = 0, buf = 0;
+    uint32_t res_par[2] = {0, 0};
+    const int cpg = P.gn_cpg;
+    const int red = cpg < 32 ? cpg : 32;  // lanes sharing a GroupNorm group inside this warp
+
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile, MBLK, 128);
+      const int c0 = t.n0 + q * 32;  // this warp's first output channel
+      const float bias_c = (P.bias_mode == T2H_BIAS_COL) ? __ldg(P.bias + c0 + lane) : 0.f;
+      auto issue_res = [&](int k, int b) {
+        mbar_expect_tx(&res_bar[q][b], kWarpTile);
+        tma_load_4d(&tmR, &res_bar[q][b], my_res + b * kWarpTile, c0, t.w0, t.h0 + k * rows_per_chunk,
+                    t.img);
+      };
+      if (has_res && lane == 0) {
+        issue_res(0, buf);
+        issue_res(1, buf ^ 1);
+      }
+      float gs = 0.f, gss = 0.f;
+      mbar_wait(&tfull_bar[as], ap);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < NCH; ++k) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + k * 32, r);
+        tmem_ld_wait();
+        if (k == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        if (P.debug & 1) {
+          if (has_res) {
+            mbar_wait(&res_bar[q][buf], res_par[buf]);
+            res_par[buf] ^= 1;
+            __syncwarp();
+            if (lane == 0 && k + 2 < NCH) issue_res(k + 2, buf);
+          }
+          buf ^= 1;
+          continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + bias_c;
+        if (P.act == T2H_ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (has_res) {
+          mbar_wait(&res_bar[q][buf], res_par[buf]);
+          res_par[buf] ^= 1;
+          const uint8_t* rb = my_res + buf * kWarpTile;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
+            v[i] += *reinterpret_cast<const float*>(rb + swz(i, lane >> 2) + ((lane & 3) << 2));
+        }
+        if (P.gn_stats) {
+          const int hrow0 = t.h0 + k * rows_per_chunk;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = (hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W);
+            const float x = ok ? v[i] : 0.f;
+            gs += x;
+            gss = fmaf(x, x, gss);
+          }
+        }
+        if (lane == 0) tma_store_wait_read<1>();  // my_out[buf]'s previous store has drained
+        __syncwarp();
+        uint8_t* ob = my_out + buf * kWarpTile;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          *reinterpret_cast<float*>(ob + swz(i, lane >> 2) + ((lane & 3) << 2)) = v[i];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmD, ob, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
+          tma_store_commit();
+          if (has_res && k + 2 < NCH) issue_res(k + 2, buf);
+        }
+        buf ^= 1;
+      }
+      if (P.gn_stats) {
+        for (int off = 1; off < red; off <<= 1) {
+          gs += __shfl_xor_sync(0xffffffffu, gs, off);
+          gss += __shfl_xor_sync(0xffffffffu, gss, off);
+        }
+        if ((lane & (red - 1)) == 0) {
+          const int g = (c0 + lane) / cpg;
+          double* dst = P.gn_stats + ((long long)t.img * P.gn_groups + g) * 2;
+          atomicAdd(dst, (double)gs);
+          atomicAdd(dst + 1, (double)gss);
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        ap ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace t2h
