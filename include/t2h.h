@@ -129,6 +129,8 @@ typedef struct t2h_tapgemm_params {
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
+/* profiling aid: copies the per-CTA counters the kernels record when T2H_DEBUG has bit 16 set */
+int t2h_debug_read(long long* out, int n);
 
 /* ------------------------------------------------------------------------
  * Layout / precision conversion (HBM-bound)

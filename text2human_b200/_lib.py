@@ -50,6 +50,7 @@ SIGNATURES = {
     "t2h_last_error": (C.c_char_p, []),
     "t2h_device_info": (_I, [C.POINTER(_I)] * 3),
     "t2h_tapgemm": (_I, [C.POINTER(TapGemmParams), _P]),
+    "t2h_debug_read": (_I, [C.POINTER(C.c_longlong), _I]),
     "t2h_nchw_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "t2h_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "t2h_nchw_to_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -52,6 +52,9 @@ struct TapGemmDev {
   int gn_cpg, gn_groups;
 };
 
+// profiling scratch (T2H_DEBUG bit 16): per CTA {MMA-thread cycles, MMAs issued, epilogue-warp cycles, tiles}
+__device__ long long g_t2h_dbg[148 * 4];
+
 constexpr int kBK = 64;                      // fp16 elements per 128-byte swizzled row
 constexpr int kABlockBytes = 128 * 128;      // one 128-row A block of a stage
 constexpr int kThreads = 256;
@@ -260,86 +263,81 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // One thread; per MMA it only adds to the two descriptor low words (see umma_ksteps), which keeps
+    // the issue stream well under the ~120 cycles an MMA occupies the tensor pipe.
+    {  // the whole warp runs the loop; one elected lane issues the tcgen05 instructions
       constexpr uint32_t IDESC = umma_idesc_f16(128, BN);
       const int last_steps = (P.C - (P.kchunks - 1) * kBK + 15) / 16;  // UMMA_K=16 steps
-      const int row_bytes = P.TW * 128;  // one image row of the slab
+      const uint32_t row16 = (uint32_t)(P.TW * 128) >> 4;  // one slab image row, in 16-byte units
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_ring));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(b_ring));
+      constexpr uint32_t A16 = C::kASlot >> 4, B16 = C::kBSlot >> 4, BLK16 = kABlockBytes >> 4;
+      const bool dbg_nomma = (P.debug & 2) != 0;
+      const int ngroups = P.ngroups, kchunks = P.kchunks;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], ap ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * C::kAccCols;
-        bool fresh = true;  // first MMA of the tile overwrites the accumulator
-        // D (+)= A_view(dyrel) * B_tile
-        auto mma_batch = [&](uint32_t a_addr, uint32_t b_addr, int dyrel, int ksteps) {
-          if (P.debug & 2) return;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint64_t bdesc = umma_desc_k128(b_addr + j * 32);
+        uint32_t acc[MBLK];
 #pragma unroll
-            for (int mb = 0; mb < MBLK; ++mb) {
-              const uint64_t adesc =
-                  umma_desc_k128(a_addr + (mb * P.TH + dyrel) * row_bytes + j * 32);
-              umma_f16(d_base + mb * BN, adesc, bdesc, IDESC, (fresh && j == 0) ? 0u : 1u);
-            }
-          }
-          fresh = false;
+        for (int mb = 0; mb < MBLK; ++mb) acc[mb] = 0;
+        // D[mb] (+)= A_view(mb, dy) * B_tile
+        auto batch = [&](uint32_t a_lo, uint32_t b_lo, int ksteps) {
+          if (dbg_nomma) return;
+#pragma unroll
+          for (int mb = 0; mb < MBLK; ++mb)
+            { if (elect_one()) umma_ksteps(d_base + mb * BN, a_lo + mb * BLK16, b_lo, IDESC, ksteps, acc[mb]); acc[mb] = 1; __syncwarp(); }
         };
-        auto adv_b = [&]() {
-          if (++sb == NB) {
-            sb = 0;
-            pb ^= 1;
-          }
-        };
-        for (int g = 0; g < P.ngroups; ++g) {
+        for (int g = 0; g < ngroups; ++g) {
           const int nt = P.g_ntaps[g];
-          for (int ch = 0; ch < P.kchunks; ++ch) {
-            const int ksteps = (ch == P.kchunks - 1) ? last_steps : 4;
+          const uint32_t dy0 = P.g_dyrel[g][0] * row16, dy1 = P.g_dyrel[g][1] * row16,
+                         dy2 = P.g_dyrel[g][2] * row16;
+          for (int ch = 0; ch < kchunks; ++ch) {
+            const int ksteps = (ch == kchunks - 1) ? last_steps : 4;
             // slab slots of this (group, chunk)
-            const int sa_hi = sa;
-            const int pa_hi = pa;
+            const int sa_hi = sa, pa_hi = pa;
             if (++sa == NA) { sa = 0; pa ^= 1; }
-            int sa_lo = sa, pa_lo = pa;
+            const int sa_lo = sa, pa_lo = pa;
             if (a_planes == 2) {
               if (++sa == NA) { sa = 0; pa ^= 1; }
             }
             mbar_wait(&a_full[sa_hi], pa_hi);
             tc_fence_after();
-            const uint32_t ahi = smem_u32(a_ring + sa_hi * C::kASlot);
-            const uint32_t alo = smem_u32(a_ring + sa_lo * C::kASlot);
+            const uint32_t ahi = a_lo0 + sa_hi * A16;
+            const uint32_t alo = a_lo0 + sa_lo * A16;
             for (int tp = 0; tp < nt; ++tp) {
-              const int dyrel = P.g_dyrel[g][tp];
+              const uint32_t dy = tp == 0 ? dy0 : (tp == 1 ? dy1 : dy2);
               if (a_planes == 1) {
                 mbar_wait(&b_full[sb], pb);
                 tc_fence_after();
-                mma_batch(ahi, smem_u32(b_ring + sb * C::kBSlot), dyrel, ksteps);
-                umma_commit(&b_empty[sb]);
-                adv_b();
+                batch(ahi + dy, b_lo0 + sb * B16, ksteps);
+                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
               } else {
-                // hi*lo
-                mbar_wait(&b_full[sb], pb);
+                mbar_wait(&b_full[sb], pb);  // B lo
                 tc_fence_after();
-                mma_batch(ahi, smem_u32(b_ring + sb * C::kBSlot), dyrel, ksteps);
-                umma_commit(&b_empty[sb]);
-                adv_b();
-                // hi*hi, then lo*hi on the same weight tile
-                mbar_wait(&b_full[sb], pb);
+                batch(ahi + dy, b_lo0 + sb * B16, ksteps);  // hi*lo
+                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
+                mbar_wait(&b_full[sb], pb);  // B hi
                 tc_fence_after();
-                const uint32_t bhi = smem_u32(b_ring + sb * C::kBSlot);
-                mma_batch(ahi, bhi, dyrel, ksteps);
-                if (tp == nt - 1) umma_commit(&a_empty[sa_hi]);  // hi slab done
+                const uint32_t bhi = b_lo0 + sb * B16;
+                batch(ahi + dy, bhi, ksteps);  // hi*hi
+                if (tp == nt - 1) { if (elect_one()) umma_commit(&a_empty[sa_hi]); __syncwarp(); }  // hi slab done
                 if (tp == 0) {
                   mbar_wait(&a_full[sa_lo], pa_lo);
                   tc_fence_after();
                 }
-                mma_batch(alo, bhi, dyrel, ksteps);
-                umma_commit(&b_empty[sb]);
-                adv_b();
+                batch(alo + dy, bhi, ksteps);  // lo*hi
+                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
               }
             }
-            umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]);
+            { if (elect_one()) umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]); __syncwarp(); }
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        { if (elect_one()) umma_commit(&tfull_bar[as]); __syncwarp(); }  // accumulator complete
         if (++as == 2) {
           as = 0;
           ap ^= 1;
@@ -734,7 +732,7 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  tapgemm_swap_kernel<MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
+  tapgemm_swap_kernel<MBLK><<<grid, kSwapThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -742,6 +740,12 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 }  // namespace t2h
 
 using namespace t2h;
+
+extern "C" int t2h_debug_read(long long* out, int n) {
+  if (n > 148 * 4) n = 148 * 4;
+  T2H_CUDA(cudaMemcpyFromSymbol(out, g_t2h_dbg, sizeof(long long) * n));
+  return T2H_OK;
+}
 
 extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   T2H_CHECK_ARG(p && p->a && p->b && p->d, "tapgemm: null operand");

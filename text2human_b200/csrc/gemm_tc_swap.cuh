@@ -19,8 +19,10 @@ namespace t2h {
 
 constexpr int kWarpTile = 32 * 128;  // 32 pixels x 32 fp32 channels
 
+constexpr int kSwapThreads = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
+
 template <int MBLK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kSwapThreads, 1)
 tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ TapGemmDev P) {
@@ -32,8 +34,8 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + NA * C::kASlot;
-  uint8_t* out_buf = b_ring + NB * C::kBSlot;     // 4 warps x 2 x 4 KB
-  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;  // 4 warps x 2 x 4 KB
+  uint8_t* out_buf = b_ring + NB * C::kBSlot;     // 8 warps x 4 KB
+  uint8_t* res_buf = out_buf + 2 * kEpiBufBytes;  // 8 warps x 4 KB
 
   __shared__ __align__(8) uint64_t a_full[kMaxSlots];
   __shared__ __align__(8) uint64_t a_empty[kMaxSlots];
@@ -41,7 +43,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t b_empty[kMaxSlots];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
-  __shared__ __align__(8) uint64_t res_bar[4][2];
+  __shared__ __align__(8) uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
@@ -64,9 +66,9 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s >> 1][s & 1], 1);
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -83,7 +85,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ---------------------------------------------- activation slab producer
-    if (lane == 0) {
+    if (lane == 0 && !(P.debug & 8)) {
       int sa = 0, pa = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, MBLK, 128);
@@ -107,7 +109,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 3) {
     // ---------------------------------------------- weight tile producer (128 couts x 64 k)
-    if (lane == 0) {
+    if (lane == 0 && !(P.debug & 8)) {
       int sb = 0, pb = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, MBLK, 128);
@@ -132,94 +134,108 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ---------------------------------------------- MMA issuer: D^T[cout, pixel] += W * slab^T
-    if (lane == 0) {
+    // One thread; everything it needs per MMA is two 32-bit adds (descriptor low words), so the
+    // issue stream stays far below the 128 cycles an M128 x N256 x K16 MMA occupies the pipe.
+    {  // the whole warp runs the loop; one elected lane issues the tcgen05 instructions
       constexpr uint32_t IDESC = umma_idesc_f16(128, NPIX);
       const int last_steps = (P.C - (P.kchunks - 1) * kBK + 15) / 16;
-      const int row_bytes = P.TW * 128;
+      const uint32_t row16 = (uint32_t)(P.TW * 128) >> 4;  // one slab image row, in 16-byte units
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_ring));
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(b_ring));
+      constexpr uint32_t A16 = C::kASlot >> 4, B16 = C::kBSlot >> 4;
+      const bool dbg_nobar = (P.debug & 8) != 0, dbg_nomma = (P.debug & 2) != 0;
+      const int ngroups = P.ngroups, kchunks = P.kchunks;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
+      long long n_mma = 0, t_wait = 0, t_exec = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const long long tw0 = clock64();
         mbar_wait(&tempty_bar[as], ap ^ 1);
+        t_wait += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * C::kAccCols;
-        bool fresh = true;
-        auto mma_batch = [&](uint32_t w_addr, uint32_t slab_addr, int dyrel, int ksteps) {
-          if (P.debug & 2) return;
-          for (int j = 0; j < ksteps; ++j) {
-            umma_f16(d_base, umma_desc_k128(w_addr + j * 32),
-                     umma_desc_k128(slab_addr + dyrel * row_bytes + j * 32), IDESC,
-                     (fresh && j == 0) ? 0u : 1u);
-          }
-          fresh = false;
-        };
-        auto adv_b = [&]() {
-          if (++sb == NB) {
-            sb = 0;
-            pb ^= 1;
-          }
-        };
-        for (int g = 0; g < P.ngroups; ++g) {
+        uint32_t acc = 0;
+        for (int g = 0; g < ngroups; ++g) {
           const int nt = P.g_ntaps[g];
-          for (int ch = 0; ch < P.kchunks; ++ch) {
-            const int ksteps = (ch == P.kchunks - 1) ? last_steps : 4;
+          const uint32_t dy0 = P.g_dyrel[g][0] * row16, dy1 = P.g_dyrel[g][1] * row16,
+                         dy2 = P.g_dyrel[g][2] * row16;
+          for (int ch = 0; ch < kchunks; ++ch) {
+            const int ksteps = (ch == kchunks - 1) ? last_steps : 4;
             const int sa_hi = sa, pa_hi = pa;
             if (++sa == NA) { sa = 0; pa ^= 1; }
             const int sa_lo = sa, pa_lo = pa;
             if (a_planes == 2) {
               if (++sa == NA) { sa = 0; pa ^= 1; }
             }
-            mbar_wait(&a_full[sa_hi], pa_hi);
+            if (!dbg_nobar) mbar_wait(&a_full[sa_hi], pa_hi);
             tc_fence_after();
-            const uint32_t ahi = smem_u32(a_ring + sa_hi * C::kASlot);
-            const uint32_t alo = smem_u32(a_ring + sa_lo * C::kASlot);
+            const uint32_t xhi = a_lo0 + sa_hi * A16;
+            const uint32_t xlo = a_lo0 + sa_lo * A16;
             for (int tp = 0; tp < nt; ++tp) {
-              const int dyrel = P.g_dyrel[g][tp];
+              const uint32_t dy = tp == 0 ? dy0 : (tp == 1 ? dy1 : dy2);
               if (a_planes == 1) {
-                mbar_wait(&b_full[sb], pb);
+                if (!dbg_nobar) mbar_wait(&b_full[sb], pb);
                 tc_fence_after();
-                mma_batch(smem_u32(b_ring + sb * C::kBSlot), ahi, dyrel, ksteps);
-                umma_commit(&b_empty[sb]);
-                adv_b();
+                if (!dbg_nomma) { if (elect_one()) umma_ksteps(d_base, b_lo0 + sb * B16, xhi + dy, IDESC, ksteps, acc); acc = 1; __syncwarp(); }
+                if (!dbg_nobar) { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
               } else {
-                mbar_wait(&b_full[sb], pb);  // w_lo
+                if (!dbg_nobar) mbar_wait(&b_full[sb], pb);  // w_lo
                 tc_fence_after();
-                mma_batch(smem_u32(b_ring + sb * C::kBSlot), ahi, dyrel, ksteps);  // x_hi * w_lo
-                umma_commit(&b_empty[sb]);
-                adv_b();
-                mbar_wait(&b_full[sb], pb);  // w_hi
+                if (!dbg_nomma) { if (elect_one()) umma_ksteps(d_base, b_lo0 + sb * B16, xhi + dy, IDESC, ksteps, acc); acc = 1; __syncwarp(); }  // x_hi*w_lo
+                if (!dbg_nobar) { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
+                if (!dbg_nobar) mbar_wait(&b_full[sb], pb);  // w_hi
                 tc_fence_after();
-                const uint32_t whi = smem_u32(b_ring + sb * C::kBSlot);
-                mma_batch(whi, ahi, dyrel, ksteps);  // x_hi * w_hi
-                if (tp == nt - 1) umma_commit(&a_empty[sa_hi]);
-                if (tp == 0) {
+                const uint32_t whi = b_lo0 + sb * B16;
+                if (!dbg_nomma) { if (elect_one()) umma_ksteps(d_base, whi, xhi + dy, IDESC, ksteps, acc); acc = 1; __syncwarp(); }  // x_hi*w_hi
+                if (tp == nt - 1 && !dbg_nobar) { if (elect_one()) umma_commit(&a_empty[sa_hi]); __syncwarp(); }
+                if (tp == 0 && !dbg_nobar) {
                   mbar_wait(&a_full[sa_lo], pa_lo);
                   tc_fence_after();
                 }
-                mma_batch(whi, alo, dyrel, ksteps);  // x_lo * w_hi
-                umma_commit(&b_empty[sb]);
-                adv_b();
+                if (!dbg_nomma) { if (elect_one()) umma_ksteps(d_base, whi, xlo + dy, IDESC, ksteps, acc); acc = 1; __syncwarp(); }  // x_lo*w_hi
+                if (!dbg_nobar) { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                if (++sb == NB) { sb = 0; pb ^= 1; }
               }
+              n_mma += ksteps * (a_planes == 2 ? 3 : 1);
             }
-            umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]);
+            if (!dbg_nobar) { if (elect_one()) umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]); __syncwarp(); }
           }
         }
-        umma_commit(&tfull_bar[as]);
+        { if (elect_one()) umma_commit(&tfull_bar[as]); __syncwarp(); }
+        if (P.debug & 128) {  // experiment: serialise — wait for this tile's MMAs before issuing more
+          mbar_wait(&tfull_bar[as], ap);
+          t_exec += clock64() - tw0;
+        }
         if (++as == 2) {
           as = 0;
           ap ^= 1;
         }
       }
+      if ((P.debug & 16) && lane == 0) {
+        g_t2h_dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
+        g_t2h_dbg[blockIdx.x * 4 + 1] = n_mma;
+        g_t2h_dbg[blockIdx.x * 4 + 2] = t_wait;
+        g_t2h_dbg[blockIdx.x * 4 + 3] = t_exec;
+      }
     }
   } else if (warp >= 4) {
     // ---------------------------------------------- per-warp transposed epilogue
+    // Two warps per TMEM lane quadrant take alternate 32-pixel chunks, so one warp's TMEM/TMA
+    // latencies hide behind the other's arithmetic.  Each warp owns one 4 KB output tile and one
+    // 4 KB residual tile in shared memory.
     const int q = warp & 3;
-    uint8_t* my_out = out_buf + q * 2 * kWarpTile;
-    uint8_t* my_res = res_buf + q * 2 * kWarpTile;
+    const int e = warp - 4;          // 0..7
+    const int half = e >> 2;         // which of the quadrant's two warps
+    uint8_t* my_out = out_buf + e * kWarpTile;
+    uint8_t* my_res = res_buf + e * kWarpTile;
     const bool has_res = P.residual != nullptr;
-    const int tw_shift = 31 - __clz(P.TW);    // TW is a power of two <= 32
+    const int tw_shift = 31 - __clz(P.TW);      // TW is a power of two <= 32
     const int rows_per_chunk = 32 >> tw_shift;  // image rows covered by 32 pixels
     constexpr int NCH = NPIX / 32;
-    int as = 0, ap = 0, buf = 0;
-    uint32_t res_par[2] = {0, 0};
+    int as = 0, ap = 0;
+    uint32_t res_par = 0;
     const int cpg = P.gn_cpg;
     const int red = cpg < 32 ? cpg : 32;  // lanes sharing a GroupNorm group inside this warp
 
@@ -227,36 +243,34 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
       const int c0 = t.n0 + q * 32;  // this warp's first output channel
       const float bias_c = (P.bias_mode == T2H_BIAS_COL) ? __ldg(P.bias + c0 + lane) : 0.f;
-      auto issue_res = [&](int k, int b) {
-        mbar_expect_tx(&res_bar[q][b], kWarpTile);
-        tma_load_4d(&tmR, &res_bar[q][b], my_res + b * kWarpTile, c0, t.w0, t.h0 + k * rows_per_chunk,
-                    t.img);
+      auto issue_res = [&](int k) {
+        mbar_expect_tx(&res_bar[e], kWarpTile);
+        tma_load_4d(&tmR, &res_bar[e], my_res, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
       };
-      if (has_res && lane == 0) {
-        issue_res(0, buf);
-        issue_res(1, buf ^ 1);
-      }
+      if (has_res && lane == 0) issue_res(half);
+      // interior tiles need no per-pixel validity test for the GroupNorm sums
+      const bool interior = (t.h0 + MBLK * P.TH <= P.H) && (t.w0 + P.TW <= P.W);
       float gs = 0.f, gss = 0.f;
       mbar_wait(&tfull_bar[as], ap);
       tc_fence_after();
 #pragma unroll 1
-      for (int k = 0; k < NCH; ++k) {
+      for (int k = half; k < NCH; k += 2) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + k * 32, r);
         tmem_ld_wait();
-        if (k == NCH - 1) {
+        if (k + 2 >= NCH) {
+          // this warp's last TMEM read of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         if (P.debug & 1) {
           if (has_res) {
-            mbar_wait(&res_bar[q][buf], res_par[buf]);
-            res_par[buf] ^= 1;
+            mbar_wait(&res_bar[e], res_par);
+            res_par ^= 1;
             __syncwarp();
-            if (lane == 0 && k + 2 < NCH) issue_res(k + 2, buf);
+            if (lane == 0 && k + 2 < NCH) issue_res(k + 2);
           }
-          buf ^= 1;
           continue;
         }
         float v[32];
@@ -267,37 +281,43 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
         }
         if (has_res) {
-          mbar_wait(&res_bar[q][buf], res_par[buf]);
-          res_par[buf] ^= 1;
-          const uint8_t* rb = my_res + buf * kWarpTile;
+          mbar_wait(&res_bar[e], res_par);
+          res_par ^= 1;
 #pragma unroll
           for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
-            v[i] += *reinterpret_cast<const float*>(rb + swz(i, lane >> 2) + ((lane & 3) << 2));
+            v[i] += *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+          __syncwarp();
+          if (lane == 0 && k + 2 < NCH) issue_res(k + 2);  // overlaps the rest of this chunk
         }
         if (P.gn_stats) {
-          const int hrow0 = t.h0 + k * rows_per_chunk;
+          if (interior) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const bool ok = (hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W);
-            const float x = ok ? v[i] : 0.f;
-            gs += x;
-            gss = fmaf(x, x, gss);
+            for (int i = 0; i < 32; ++i) {
+              gs += v[i];
+              gss = fmaf(v[i], v[i], gss);
+            }
+          } else {
+            const int hrow0 = t.h0 + k * rows_per_chunk;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const bool ok = (hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W);
+              const float x = ok ? v[i] : 0.f;
+              gs += x;
+              gss = fmaf(x, x, gss);
+            }
           }
         }
-        if (lane == 0) tma_store_wait_read<1>();  // my_out[buf]'s previous store has drained
+        if (lane == 0) tma_store_wait_read<0>();  // my_out's previous store has drained
         __syncwarp();
-        uint8_t* ob = my_out + buf * kWarpTile;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          *reinterpret_cast<float*>(ob + swz(i, lane >> 2) + ((lane & 3) << 2)) = v[i];
+          *reinterpret_cast<float*>(my_out + swz(i, lane >> 2) + ((lane & 3) << 2)) = v[i];
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&tmD, ob, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
+          tma_store_4d(&tmD, my_out, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
           tma_store_commit();
-          if (has_res && k + 2 < NCH) issue_res(k + 2, buf);
         }
-        buf ^= 1;
       }
       if (P.gn_stats) {
         for (int off = 1; off < red; off <<= 1) {

@@ -179,10 +179,50 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor split for tight issue loops: a constant high word and a low word that advances
+// by (bytes >> 4) — +2 per UMMA_K=16 step of fp16 inside the 128-byte swizzled row.
+constexpr uint32_t kUmmaDescHiK128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) {
+  return (static_cast<uint64_t>(kUmmaDescHiK128) << 32) | lo;
+}
+// `ksteps` (<= 4) K=16 steps of D (+)= A*B; acc is 0 only for the very first MMA of an accumulator.
+__device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            int ksteps, uint32_t& acc) {
+  if (ksteps == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      umma_f16(d_tmem, umma_desc_join(a_lo + 2 * j), umma_desc_join(b_lo + 2 * j), idesc, acc);
+      acc = 1;
+    }
+  } else {
+    for (int j = 0; j < ksteps; ++j) {
+      umma_f16(d_tmem, umma_desc_join(a_lo + 2 * j), umma_desc_join(b_lo + 2 * j), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 accumulate
 // (c_format 1, bits [4,6)), both K-major, N>>3 at bits [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// one lane of a fully converged warp (warp-uniform control flow keeps the issue loop on the uniform
+// datapath; only the tcgen05 instruction itself is predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ------------------------------------------------------------ misc helpers

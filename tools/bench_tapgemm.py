@@ -28,6 +28,17 @@ def bench_conv(N, H, W, Cin, Cout, terms, residual, stats, iters=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = 2.0 * N * H * W * Cout * Cin * 9
+    if int(os.environ.get("T2H_DEBUG", "0")) & 16:
+        import ctypes
+        from text2human_b200 import _lib
+        buf = (ctypes.c_longlong * (148 * 4))()
+        _lib.load().t2h_debug_read(buf, 148 * 4)
+        cyc = max(buf[i * 4] for i in range(148))
+        nm = max(buf[i * 4 + 1] for i in range(148))
+        tw = max(buf[i * 4 + 2] for i in range(148))
+        tx = max(buf[i * 4 + 3] for i in range(148))
+        print(f"    MMA thread: {cyc} cycles, {nm} MMAs -> {cyc / max(nm, 1):.1f} cyc/MMA, waited on epilogue {tw} cyc; "
+              f"eff clock {cyc / (ms * 1e-3) / 1e9:.2f} GHz; serialised exec {tx} cyc ({tx / max(nm, 1):.1f}/MMA)")
     return ms, fl / ms / 1e9
 
 

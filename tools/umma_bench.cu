@@ -40,12 +40,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 
 // out[blockIdx] = cycles for `reps` batches of (4 * nacc) MMAs
 template <int N>
-__global__ void __launch_bounds__(128, 1) bench_1cta(long long* out, int reps, int nacc, int kst) {
+__global__ void __launch_bounds__(128, 1) bench_1cta(long long* out, int reps, int nacc, int kst, int rnd) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_s;
-  for (int i = threadIdx.x; i < (16384 * 2 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < (16384 * 2 + N * 128) / 4; i += blockDim.x) {
+    uint32_t h = (i + 1) * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    // two fp16 values in [-2,2): sign|exp in {13..15}|mantissa random
+    uint32_t v = (h & 0x83FF83FFu) | 0x34003400u | ((h >> 4) & 0x08000800u);
+    reinterpret_cast<uint32_t*>(smem)[i] = rnd ? v : 0u;
+  }
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(128, 1) bench_1cta(long long* out, int reps, i
     for (int r = 0; r < reps; ++r) {
       for (int acc = 0; acc < nacc; ++acc)
         for (int j = 0; j < kst; ++j)
-          umma_f16(tm + acc * N, umma_desc_k128(a + acc * 16384 + (j & 3) * 32), umma_desc_k128(b + (j & 3) * 32), idesc, 1);
+          umma_f16(tm + acc * N, umma_desc_k128(a + acc * 16384 + (j & 3) * 32), umma_desc_k128(b + (j & 3) * 32), idesc, j > 0);
     }
     umma_commit(&bar);
     mbar_wait(&bar, par);
@@ -89,12 +95,17 @@ __global__ void __launch_bounds__(128, 1) bench_1cta(long long* out, int reps, i
 
 template <int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-bench_2cta(long long* out, int reps, int nacc, int kst) {
+bench_2cta(long long* out, int reps, int nacc, int kst, int rnd) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_s;
-  for (int i = threadIdx.x; i < (16384 * 2 + N * 64) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < (16384 * 2 + N * 64) / 4; i += blockDim.x) {
+    uint32_t h = (i + 1) * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    uint32_t v = (h & 0x83FF83FFu) | 0x34003400u | ((h >> 4) & 0x08000800u);
+    reinterpret_cast<uint32_t*>(smem)[i] = rnd ? v : 0u;
+  }
   const uint32_t rank = cluster_ctarank();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
@@ -124,7 +135,7 @@ bench_2cta(long long* out, int reps, int nacc, int kst) {
     for (int r = 0; r < reps; ++r) {
       for (int acc = 0; acc < nacc; ++acc)
         for (int j = 0; j < kst; ++j)
-          umma_f16_2cta(tm + acc * N, umma_desc_k128(a + acc * 16384 + (j & 3) * 32), umma_desc_k128(b + (j & 3) * 32), idesc, 1);
+          umma_f16_2cta(tm + acc * N, umma_desc_k128(a + acc * 16384 + (j & 3) * 32), umma_desc_k128(b + (j & 3) * 32), idesc, j > 0);
     }
     umma_commit_2cta(&bar);
     mbar_wait(&bar, par);
@@ -141,18 +152,27 @@ bench_2cta(long long* out, int reps, int nacc, int kst) {
 }
 
 template <typename K>
-static void run(const char* name, K kern, int grid, int n, int m_total, int reps, int nacc, int kst, bool pair) {
+static void run(const char* name, K kern, int grid, int n, int m_total, int reps, int nacc, int kst, bool pair,
+                int rnd) {
   long long* d;
   cudaMalloc(&d, sizeof(long long) * grid);
   cudaMemset(d, 0, sizeof(long long) * grid);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  kern<<<grid, 128, 200 * 1024>>>(d, reps, nacc, kst);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  kern<<<grid, 128, 200 * 1024>>>(d, reps / 10, nacc, kst, rnd);  // warm
+  cudaEventRecord(e0);
+  kern<<<grid, 128, 200 * 1024>>>(d, reps, nacc, kst, rnd);
+  cudaEventRecord(e1);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("%-28s FAILED: %s\n", name, cudaGetErrorString(e));
     cudaFree(d);
     return;
   }
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
   long long h[512];
   int cnt = pair ? grid / 2 : grid;
   cudaMemcpy(h, d, sizeof(long long) * cnt, cudaMemcpyDeviceToHost);
@@ -161,8 +181,9 @@ static void run(const char* name, K kern, int grid, int n, int m_total, int reps
   const double mmas = (double)reps * nacc * kst;
   const double cyc = (double)mx / mmas;
   const double macs = (double)m_total * n * 16;
-  printf("%-28s grid=%3d  %8.1f cyc/MMA  -> %7.1f MAC/clk per SM (nominal peak 4096)\n", name, grid, cyc,
-         macs / cyc / (pair ? 2 : 1));
+  const double tflops = 2.0 * macs * mmas * cnt / (ms * 1e-3) / 1e12;
+  printf("%-22s %s grid=%3d %7.1f cyc/MMA %7.1f MAC/clk/SM  %8.3f ms  %7.1f TFLOP/s  (eff clk %.2f GHz)\n", name,
+         rnd ? "rand" : "zero", grid, cyc, macs / cyc / (pair ? 2 : 1), ms, tflops, mx / (ms * 1e-3) / 1e9);
   cudaFree(d);
 }
 
@@ -170,17 +191,15 @@ int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
   printf("%s, %d SMs\n", p.name, p.multiProcessorCount);
-  const int reps = 2000;
-  for (int grid : {1, 148}) {
-    run("1cta M128 N64  1acc", bench_1cta<64>, grid, 64, 128, reps, 1, 4, false);
-    run("1cta M128 N128 1acc", bench_1cta<128>, grid, 128, 128, reps, 1, 4, false);
-    run("1cta M128 N128 2acc", bench_1cta<128>, grid, 128, 128, reps, 2, 4, false);
-    run("1cta M128 N256 1acc", bench_1cta<256>, grid, 256, 128, reps, 1, 4, false);
-    run("1cta M128 N256 2acc", bench_1cta<256>, grid, 256, 128, reps, 2, 4, false);
-    run("2cta M256 N128 1acc", bench_2cta<128>, grid == 1 ? 2 : 148, 128, 256, reps, 1, 4, true);
-    run("2cta M256 N128 2acc", bench_2cta<128>, grid == 1 ? 2 : 148, 128, 256, reps, 2, 4, true);
-    run("2cta M256 N256 1acc", bench_2cta<256>, grid == 1 ? 2 : 148, 256, 256, reps, 1, 4, true);
-    run("2cta M256 N256 2acc", bench_2cta<256>, grid == 1 ? 2 : 148, 256, 256, reps, 2, 4, true);
+  const int reps = 20000;
+  for (int rnd : {0, 1}) {
+    const int grid = 148;
+    run("1cta M128 N128 2acc", bench_1cta<128>, grid, 128, 128, reps, 2, 4, false, rnd);
+    run("1cta M128 N256 1acc", bench_1cta<256>, grid, 256, 128, reps, 1, 4, false, rnd);
+    run("1cta M128 N256 2acc", bench_1cta<256>, grid, 256, 128, reps, 2, 4, false, rnd);
+    run("2cta M256 N128 2acc", bench_2cta<128>, grid, 128, 256, reps, 2, 4, true, rnd);
+    run("2cta M256 N256 1acc", bench_2cta<256>, grid, 256, 256, reps, 1, 4, true, rnd);
+    run("2cta M256 N256 2acc", bench_2cta<256>, grid, 256, 256, reps, 2, 4, true, rnd);
   }
   return 0;
 }
