@@ -1,0 +1,64 @@
+"""world_size-2 gloo test (CPU) of the replica sharding used for N>1 runs: every image is processed by
+exactly one rank, the gathered result equals the single-process result, and the timing reduction takes
+the slowest rank."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+from text2human_b200 import dist as D
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    r, lr, w = D.init("gloo")
+    assert (r, w) == (rank, world)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 3, 4, 4, generator=g)        # 7 images over 2 ranks: 4 + 3
+    m = torch.arange(7).float().view(7, 1, 1, 1)
+    xs, ms = D.shard_batch((x, m), rank, world)
+    y = xs * 2 + ms                                  # stand-in for the per-image (collective-free) path
+    full = D.gather_concat(y)
+    D.barrier()
+    t = D.max_over_ranks(1.0 + rank)
+    n = D.sum_over_ranks(xs.shape[0])
+    if rank == 0:
+        q.put((full, t, n, xs.shape[0]))
+    torch.distributed.destroy_process_group()
+
+
+def test_replica_sharding_two_ranks_gloo():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    full, t, n, n0 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 3, 4, 4, generator=g)
+    want = x * 2 + torch.arange(7).float().view(7, 1, 1, 1)
+    assert torch.equal(full, want)
+    assert t == 2.0 and n == 7 and n0 == 4
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 5, 16, 17):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                a, b = D.shard_range(n, r, world)
+                assert 0 <= a <= b <= n
+                seen += list(range(a, b))
+            assert seen == list(range(n))

@@ -159,3 +159,93 @@ def test_vq_pipeline_config1_matches_oracle(cuda):
         ref_dec = vqgan_ref.decoder(sd, vqgan_ref.conv(sd, "post_quant_conv", want["quant"], padding=0), "decoder.")
     assert _rel(dec_tf, ref_dec) < TOL_EXACT
     assert abs(loss.item() - want["loss"].item()) <= 1e-3 * abs(want["loss"].item())
+
+
+HIER_OPT = dict(embed_dim=256, n_embed=1024, codebook_spatial_size=2, bot_n_embed=512, bot_double_z=False,
+                bot_z_channels=256, bot_resolution=512, bot_in_channels=3, bot_out_ch=3, bot_ch=128,
+                bot_ch_mult=[1, 1, 2, 4], bot_num_res_blocks=2, bot_attn_resolutions=[64], bot_dropout=0.0,
+                top_double_z=False, top_z_channels=256, top_resolution=512, top_in_channels=3, top_out_ch=3,
+                top_ch=128, top_ch_mult=[1, 1, 2, 2, 4], top_num_res_blocks=2, top_attn_resolutions=[32],
+                top_dropout=0.0)
+
+
+def test_hierarchy_forward_step_matches_oracle(cuda):
+    """BASELINE config 3 nets (vqvae_top + vqvae_bottom) on a 128x64 crop: top/bottom latents, both index
+    maps and the residual decode against the torch fp32 oracle (hierarchy_vqgan_model.py:215-239)."""
+    from oracle import vqgan_ref
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import HierarchyVQSpatialTextureAwareModel
+    ops.set_precision("fp32")
+    torch.manual_seed(7)
+    m = HierarchyVQSpatialTextureAwareModel(HIER_OPT)
+    cbt = R.codebooks(8, 18, 1024, 256, "trained")
+    cbb = R.codebooks(9, 18, 512, 1024, "trained")
+    for k in range(18):
+        m.top_quantize.embedding_list[k].weight.data.copy_(cbt[k])
+        m.bot_quantize.embedding_list[k].weight.data.copy_(cbb[k])
+    m = m.to(cuda).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x = R.image(3, 2, 3, 128, 64).to(cuda)
+    mask = R.blocky_mask(3, 2, 128, 64, 16).to(cuda)
+    with torch.no_grad():
+        want = vqgan_ref.hierarchy_forward_step(sd, cbt.to(cuda), cbb.to(cuda), x, mask)
+    dec, loss, info = m.forward_step(x, mask, return_info=True)
+    top_ok = (info["top_idx"] == want["top_idx"]).float().mean().item()
+    bot_ok = (info["bot_idx"].reshape(-1) == want["bot_idx"].reshape(-1)).float().mean().item()
+    assert top_ok >= 0.98 and bot_ok >= 0.98, (top_ok, bot_ok)
+    if top_ok == 1.0 and bot_ok == 1.0:
+        assert _rel(dec, want["dec"]) < TOL_EXACT
+        assert abs(loss.item() - want["loss"].item()) <= 1e-3 * abs(want["loss"].item())
+    # module-level API (NCHW in/out) of the pieces the reference wrapper calls, teacher-forced
+    with torch.no_grad():
+        zt = vqgan_ref.conv(sd, "top_quant_conv", vqgan_ref.encoder(sd, x, "top_encoder."), padding=0)
+        zb = vqgan_ref.conv(sd, "bot_quant_conv", vqgan_ref.encoder(sd, x, "bot_encoder."), padding=0)
+        qt, _, _, _ = vqgan_ref.quantize_texture(cbt.to(cuda), zt, mask)
+        qb, _, _, _ = vqgan_ref.quantize_texture(cbb.to(cuda), zb, mask, ps=2, cont_stride=512)
+        qt = vqgan_ref.conv(sd, "top_post_quant_conv", qt, padding=0)
+        res = vqgan_ref.decoder_res(sd, vqgan_ref.conv(sd, "bot_post_quant_conv", qb, padding=0), "bot_decoder_res.")
+        ref_dec = vqgan_ref.decoder(sd, qt, "decoder.", bot_h=res)
+    assert _rel(m.bot_encoder(x), vqgan_ref.encoder(sd, x, "bot_encoder.")) < TOL_EXACT
+    assert _rel(m.bot_decoder_res(vqgan_ref.conv(sd, "bot_post_quant_conv", qb, padding=0)), res) < TOL_EXACT
+    assert _rel(m.decode(qt, res), ref_dec) < TOL_EXACT
+
+
+SAMPLER_OPT = dict(codebook_size=18432, segm_codebook_size=1024, texture_codebook_size=18, bert_n_emb=512,
+                   bert_n_layers=24, bert_n_head=8, block_size=512, latent_shape=[32, 16], embd_pdrop=0.0,
+                   resid_pdrop=0.0, attn_pdrop=0.0, num_head=18, sample_steps=256)
+
+
+def test_sampler_transformer_logits_and_sampling_loop(cuda, mode):
+    """BASELINE config 4 transformer (24 x 512, 18 heads): logits vs the torch fp32 oracle on a masked /
+    unmasked token mix (teacher-forced parity), then the sampling loop's structural contract."""
+    from oracle import transformer_ref
+    from text2human_b200.pipeline import Sampler
+    torch.manual_seed(11)
+    s = Sampler(SAMPLER_OPT)
+    with torch.no_grad():  # the reference leaves pos_emb at zero; make it matter for the test
+        s.sampler_fn.pos_emb.normal_(0, 0.02)
+    s = s.to(cuda).eval()
+    sd = {k: v.detach() for k, v in s.sampler_fn.state_dict().items()}
+    B, T = 2, 512
+    g = torch.Generator().manual_seed(5)
+    tex = torch.randint(0, 18, (B, T), generator=g)
+    idx = torch.where(torch.rand(B, T, generator=g) < 0.5, torch.full((B, T), 18432),
+                      torch.randint(0, 1024, (B, T), generator=g) + 1024 * tex).to(cuda)
+    segm = torch.randint(0, 1024, (B, T), generator=g).to(cuda)
+    tex = tex.to(cuda)
+    with torch.no_grad():
+        want = torch.stack(transformer_ref.transformer_logits(sd, idx, segm, tex, n_head=8), 2)
+    got = s.sampler_fn.forward_logits(idx, segm, tex)
+    assert got.shape == (B, T, 18, 1024)
+    assert _rel(got, want) < _tol(mode)
+    lst = s.sampler_fn(idx, segm, tex)
+    assert len(lst) == 18 and lst[3].shape == (B, T, 1024) and torch.equal(lst[3], got[:, :, 3])
+    if mode == "fp32":
+        mask = R.blocky_mask(4, B, 512, 256, 64).to(cuda)
+        gen = torch.Generator(device=cuda).manual_seed(2021)
+        out, x_t = s.sample_fn(segm, mask, sample_steps=6, generator=gen)
+        texm = torch.nn.functional.interpolate(mask, (32, 16), mode="nearest").view(B, -1).long()
+        assert (x_t != 18432).all(), "every position must be unmasked after the last step"
+        assert ((x_t // 1024) == texm).all(), "tokens must come from the position's own texture codebook"
+        for k in range(18):
+            assert ((out[k] >= 0) == (texm == k)).all() and out[k].max() < 1024
