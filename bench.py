@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay one captured CUDA graph per step (measured: no gain for this GPU-bound step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -179,7 +181,7 @@ def main():
 
     import torch.distributed as dist
     from text2human_b200 import _lib, ops
-    from text2human_b200.pipeline import VQImageSegmTextureModel
+    from text2human_b200.pipeline import GraphedStep, VQImageSegmTextureModel
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
@@ -214,9 +216,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    # One step = one forward_step (~340 asynchronous launches; --graph replays them as one CUDA graph).
+    def raw_step(x, m):
+        dec, loss = model.forward_step(x, m)
+        return dec, loss
+    step = GraphedStep(raw_step, (xs_d[0], ms_d[0])) if args.graph else raw_step
+
     # ---------------- device-resident throughput (`value`) ----------------
     for i in range(args.warmup):
-        model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+        step(xs_d[i % n_var], ms_d[i % n_var])
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -225,7 +233,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        dec, loss = model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+        dec, loss = step(xs_d[i % n_var], ms_d[i % n_var])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -234,11 +242,14 @@ def main():
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---------------- end to end through the public API with host buffers ----------------
+    x_in = torch.empty_like(xs_d[0])
+    m_in = torch.empty_like(ms_d[0])
+
     def e2e_step(i):
-        x = xs_h[i % n_var].to(dev, non_blocking=True)
-        m = ms_h[i % n_var].to(dev, non_blocking=True)
-        dec, loss = model.forward_step(x, m)
-        out_h.copy_(dec, non_blocking=True)
+        x_in.copy_(xs_h[i % n_var], non_blocking=True)   # pinned host -> device, inside the timed region
+        m_in.copy_(ms_h[i % n_var], non_blocking=True)
+        dec, loss = step(x_in, m_in)
+        out_h.copy_(dec, non_blocking=True)              # device -> pinned host
         return loss
     for i in range(2):
         e2e_step(i)
@@ -296,7 +307,8 @@ def main():
                     config=dict(workload="vqvae_top.yml batch=16 512x256 encode-quantize-decode, codebook 18x1024x256",
                                 batch_per_gpu=B, precision=args.precision, parallelism=f"replicas x{world}",
                                 l2="activation working set (>2 GB/step) exceeds the 126 MB L2; inputs rotate "
-                                   "over 3 distinct batches"),
+                                   "over 3 distinct batches",
+                                launch="CUDA graph replay of one forward_step" if args.graph else "per-kernel, asynchronous"),
                     clocks=clk,
                     e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps),

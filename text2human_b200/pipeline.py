@@ -154,6 +154,36 @@ class HierarchyVQSpatialTextureAwareModel(nn.Module):
         return self.decoder.forward_nhwc(quant_top, bot_h=res)
 
 
+class GraphedStep:
+    """Capture a fixed-shape, allocation-stable sequence of libt2h launches into a CUDA graph and replay
+    it (CUDA streams + graphs instead of a tracing compiler).  ``fn(*static_inputs) -> tensor | tuple``.
+    Inputs are copied into static buffers before each replay; outputs are static buffers (clone them
+    if they must outlive the next replay)."""
+
+    def __init__(self, fn, example_inputs, warmup=2):
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):  # first calls configure kernels (cudaFuncSetAttribute) and caches
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = ops.COUNTERS["launches"]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+        self.launches = ops.COUNTERS["launches"] - before  # libt2h kernels per replay
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        ops.COUNTERS["launches"] += self.launches
+        return self.static_out
+
+
 class Sampler(nn.Module):
     """The absorbing-diffusion sampling loop of BaseSampleModel (sample_model.py:256-328) around
     TransformerMultiHead, without the reference's per-codebook host synchronisations.
@@ -174,9 +204,26 @@ class Sampler(nn.Module):
         self.shape = tuple(opt['latent_shape'])
         self.mask_id = opt['codebook_size']
         self.sample_steps = opt['sample_steps']
+        self._graphs = {}
+
+    def _logits_fn(self, B, T, device, use_graph):
+        """the transformer forward for fixed (B, T): ~240 small launches per step are CPU-launch-bound, so
+        they are captured once into a CUDA graph and replayed every diffusion step"""
+        m = self.sampler_fn
+        if not use_graph:
+            return m.forward_logits
+        key = (B, T, str(device), ops.get_terms())
+        g = self._graphs.get(key)
+        if g is None:
+            ex = (torch.full((B, T), self.mask_id, dtype=torch.long, device=device),
+                  torch.zeros((B, T), dtype=torch.long, device=device),
+                  torch.zeros((B, T), dtype=torch.long, device=device))
+            g = GraphedStep(m.forward_logits, ex)
+            self._graphs[key] = g
+        return g
 
     @torch.no_grad()
-    def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None):
+    def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None, use_graph=True):
         """segm_tokens int64 [B, T]; texture_mask float [B,1,H,W] of ids 0..17.
         Returns (list of 18 int64 [B,T] per-codebook index maps with -1 elsewhere, final x_t)."""
         m = self.sampler_fn
@@ -191,11 +238,12 @@ class Sampler(nn.Module):
         tex_c = tex.clamp(0, nh - 1)
         gather_idx = tex_c.view(B, T, 1, 1).expand(B, T, 1, ncls)
         valid_tex = (tex >= 0) & (tex < nh)
+        logits_fn = self._logits_fn(B, T, dev, use_graph)
         for t in range(steps, 0, -1):
             changes = torch.rand((B, T), device=dev, generator=generator) < (1.0 / t)
             changes = changes & ~unmasked
             unmasked = unmasked | changes
-            logits = m.forward_logits(x_t, segm_tokens, tex_c)  # [B,T,nh,ncls]
+            logits = logits_fn(x_t, segm_tokens, tex_c)  # [B,T,nh,ncls]
             own = logits.gather(2, gather_idx).view(B * T, ncls)  # each position's own texture head
             probs = torch.softmax(own / temp, dim=-1)
             draw = torch.multinomial(probs, 1, True, generator=generator).view(B, T)
