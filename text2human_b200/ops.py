@@ -182,6 +182,61 @@ def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False, want
     return out
 
 
+def pack_upsample_conv_weight(w, terms):
+    """Weights of `nearest x2 upsample -> 3x3 conv` (Upsample, vqgan_arch.py:529-534) folded into four
+    2x2 convs on the low-resolution input, one per output parity (a, b):
+        out[2i+a, 2j+b] = sum_{r,s in 0..1} Wab[r,s] . in[i + a + r - 1, j + b + s - 1]
+    with Wab[r,s] = sum of the 3x3 taps that read that input pixel (rows: a=0 -> {w0 | w1+w2},
+    a=1 -> {w0+w1 | w2}; columns likewise).  36 tap-GEMMs at high resolution become 16 at low
+    resolution (2.25x fewer FLOPs, 4x fewer activation bytes).  Returns planes [T, 16, Cout, Cin],
+    tap index = ((a*2+b)*2 + r)*2 + s."""
+    w = w.detach().float()
+    Cout, Cin = w.shape[:2]
+    rows = {0: (w[:, :, 0], w[:, :, 1] + w[:, :, 2]), 1: (w[:, :, 0] + w[:, :, 1], w[:, :, 2])}  # [Cout,Cin,3(kw)]
+    taps = []
+    for a in (0, 1):
+        for b in (0, 1):
+            for r in (0, 1):
+                wr = rows[a][r]
+                cols = (wr[:, :, 0], wr[:, :, 1] + wr[:, :, 2]) if b == 0 else (wr[:, :, 0] + wr[:, :, 1], wr[:, :, 2])
+                for sidx in (0, 1):
+                    taps.append(cols[sidx])
+    wt = torch.stack(taps)  # [16, Cout, Cin]
+    cp = (Cin + 7) // 8 * 8
+    if cp != Cin:
+        wt = torch.nn.functional.pad(wt, (0, cp - Cin))
+    return split_planes(wt, terms)
+
+
+def upsample_conv3x3(a, w16, bias, *, want_stats=False):
+    """nearest x2 + 3x3 conv on low-resolution planes a [T,N,H,W,C] with pack_upsample_conv_weight()
+    weights [T,16,Cout,C] -> fp32 NHWC [N,2H,2W,Cout] (+ fused GroupNorm statistics): four strided-output
+    launches, one per output parity."""
+    _need_cuda(a, w16)
+    T, N, H, W, Cc = a.shape
+    Cout = w16.shape[2]
+    assert w16.shape[1] == 16 and w16.shape[3] == Cc
+    H2, W2 = 2 * H, 2 * W
+    out = torch.empty((N, H2, W2, Cout), dtype=torch.float32, device=a.device)
+    stats, cpg = _stats_for(Cout, N, a.device, want_stats)
+    for pa in (0, 1):
+        for pb in (0, 1):
+            par = pa * 2 + pb
+            taps = tuple((pa + r - 1, pb + sidx - 1, 0) for r in (0, 1) for sidx in (0, 1))
+            wv = w16[:, par * 4:(par + 1) * 4]  # [T,4,Cout,C] view: plane stride stays 16 taps
+            dview = out[:, pa::2, pb::2, :]
+            _tapgemm(a=a, a_term_imgs=N, a_imgs=T * N, a_bcast=0, n_img=N, H=H, W=W, a_H=H, a_W=W, Cc=Cc,
+                     a_sw=Cc, a_sh=W * Cc, a_sn=H * W * Cc,
+                     b=wv, b_term_g=16, b_groups=(w16.shape[0] - 1) * 16 + 4, b_batched=0, n_out=Cout, b_sn=Cc,
+                     b_sg=Cout * Cc,
+                     taps=taps, d=dview, d_mode=OUT_F32,
+                     d_strides=(H2 * W2 * Cout, 2 * W2 * Cout, 2 * Cout, 1),
+                     bias=bias, bias_mode=BIAS_COL, gn_stats=stats, gn_cpg=cpg)
+    if want_stats:
+        return out, stats
+    return out
+
+
 def conv1x1(a, w, bias, *, residual=None, planes_out=False, want_stats=False):
     """1x1 conv on planes [T,N,H,W,C] with a pack_linear_weight()-packed weight [T,1,Cout,C]; tiles stay
     inside one image so GroupNorm statistics can be fused."""

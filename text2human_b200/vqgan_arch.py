@@ -99,8 +99,12 @@ class Upsample(nn.Module):
     def _fwd(self, act):
         if not self.with_conv:
             raise NotImplementedError("Upsample(with_conv=False) is not on the Text2Human path")
-        a = ops.f32_to_planes(act.x, CVT_UP2X)  # the x2 replication happens in the fp16 split pass
-        return _Act(*ops.conv3x3(a, _conv_w(self.conv), _f32(self.conv.bias), want_stats=True))
+        # nearest x2 + 3x3 conv == four 2x2 convs on the low-resolution input (one per output parity)
+        t = ops.get_terms()
+        w16 = _cached(self.conv, ("wup", t), (self.conv.weight,),
+                      lambda: ops.pack_upsample_conv_weight(self.conv.weight, t))
+        a = ops.f32_to_planes(act.x, CVT_PLAIN)
+        return _Act(*ops.upsample_conv3x3(a, w16, _f32(self.conv.bias), want_stats=True))
 
     def forward_nhwc(self, x):
         return self._fwd(_Act(x)).x
