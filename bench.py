@@ -126,6 +126,65 @@ def cpu_port_rate(threads, runs, batch=1):
     return batch / min(times), batch / (sum(times) / len(times)), times
 
 
+HIER_OPT = dict(embed_dim=256, n_embed=1024, codebook_spatial_size=2, bot_n_embed=512, bot_double_z=False,
+                bot_z_channels=256, bot_resolution=512, bot_in_channels=3, bot_out_ch=3, bot_ch=128,
+                bot_ch_mult=[1, 1, 2, 4], bot_num_res_blocks=2, bot_attn_resolutions=[64], bot_dropout=0.0,
+                top_double_z=False, top_z_channels=256, top_resolution=512, top_in_channels=3, top_out_ch=3,
+                top_ch=128, top_ch_mult=[1, 1, 2, 2, 4], top_num_res_blocks=2, top_attn_resolutions=[32],
+                top_dropout=0.0)
+SAMPLER_OPT = dict(codebook_size=18432, segm_codebook_size=1024, texture_codebook_size=18, bert_n_emb=512,
+                   bert_n_layers=24, bert_n_head=8, block_size=512, latent_shape=[32, 16], embd_pdrop=0.0,
+                   resid_pdrop=0.0, attn_pdrop=0.0, num_head=18, sample_steps=256)
+
+
+def side_workloads(dev, precision):
+    """BASELINE configs 3 and 4, a few iterations each (reported next to the headline, not instead of it)."""
+    import contextlib
+    import golden_recipes as R
+    from text2human_b200.pipeline import HierarchyVQSpatialTextureAwareModel, Sampler
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        torch.manual_seed(3)
+        with contextlib.redirect_stdout(sys.stderr):
+            hm = HierarchyVQSpatialTextureAwareModel(HIER_OPT).to(dev).eval()
+        x = R.image(7, 8, 3, 512, 256).to(dev)
+        m = R.blocky_mask(7, 8, 512, 256, 32).to(dev)
+        for _ in range(2):
+            hm.forward_step(x, m)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            hm.forward_step(x, m)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out["config3_hierarchy_forward_step"] = dict(batch=8, ms_per_step=ms, img_per_s=8 / (ms / 1e3),
+                                                     algorithmic_tflops=8 * 1200.9 / ms, precision=precision)
+        del hm
+        torch.cuda.empty_cache()
+        torch.manual_seed(4)
+        sm = Sampler(SAMPLER_OPT).to(dev).eval()
+        segm = torch.randint(0, 1024, (4, 512), device=dev)
+        tm = R.blocky_mask(9, 4, 512, 256, 64).to(dev)
+        gen = torch.Generator(device=dev).manual_seed(2021)
+        sm.sample_fn(segm, tm, sample_steps=4, generator=gen)
+        torch.cuda.synchronize()
+        steps = 32
+        e0.record()
+        sm.sample_fn(segm, tm, sample_steps=steps, generator=gen)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["config4_sampler"] = dict(batch=4, ms_per_diffusion_step=ms, measured_steps=steps,
+                                      tokens_per_s_256_steps=2048 / (ms * 256 / 1e3), extrapolated=True,
+                                      algorithmic_tflops=4 * 99.86 / ms, precision=precision,
+                                      launch="CUDA graph replay of the transformer forward per step")
+    except Exception as exc:  # side measurements must never break the headline line
+        out["error"] = repr(exc)
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (PyTorch fp32, oracle port), rank 0 only."""
     if rank != 0:
@@ -171,6 +230,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the short config-3 (hierarchy) and config-4 (sampler) side measurements")
     ap.add_argument("--graph", action="store_true",
                     help="replay one captured CUDA graph per step (measured: no gain for this GPU-bound step)")
     args = ap.parse_args()
@@ -300,6 +361,11 @@ def main():
                     note="algorithmic FLOPs = 2*MAC of the reference op graph; in fp32 mode each product is "
                          "issued as 3 fp16 tensor-core products (hi*hi+hi*lo+lo*hi), see issued_*")
 
+    # ---------------- side measurements: BASELINE configs 3 and 4 (rank 0, N=1 only) ----------------
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = side_workloads(dev, args.precision)
+
     if world > 1:
         dist.barrier()
 
@@ -324,7 +390,7 @@ def main():
                     clocks=clk,
                     e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, extra=extra,
                     pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
                     pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
         print(json.dumps(line), flush=True)

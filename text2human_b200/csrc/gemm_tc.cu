@@ -795,6 +795,12 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
               reinterpret_cast<uintptr_t>(p->d) % 16 == 0 &&
               (!p->residual || reinterpret_cast<uintptr_t>(p->residual) % 16 == 0) &&
               (!p->gn_stats || (p->gn_cpg >= 1 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0));
+  // ... and with a direct (strided) epilogue for small-Cout convs writing NCHW (conv_out): the weight
+  // tile is zero-padded to 128 rows by TMA, the 256-pixel N operand still issues at full rate.
+  const bool swap_direct = !swap && !rows_mode && TW <= 16 && p->n_out <= 128 && p->d_mode == T2H_OUT_F32 &&
+                           p->d_sc != 1 && p->bias_mode != T2H_BIAS_ROW && !p->a_bcast && !p->b_batched &&
+                           !p->b_batched_h && !p->residual && !p->gn_stats && p->act == T2H_ACT_NONE;
+  if (swap_direct) swap = true;
   {
     static int no_swap = -1;
     if (no_swap < 0) {
@@ -808,7 +814,8 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   int MBLK = 1;
   if (swap) {
     BN = 128;
-    const long long tiles2 = (long long)p->n_img * ceil_div(p->H, 2 * TH) * ceil_div(p->W, TW) * (p->n_out / 128);
+    const long long tiles2 =
+        (long long)p->n_img * ceil_div(p->H, 2 * TH) * ceil_div(p->W, TW) * ceil_div(p->n_out, 128);
     MBLK = (p->H >= 2 * TH && tiles2 >= 48) ? 2 : 1;
   } else if (BN == 128 && p->H >= 2 * TH && !p->tile_rows) {
     long long tiles1 = (long long)p->n_img * ceil_div(p->H, TH) * ceil_div(p->W, TW);
@@ -875,7 +882,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   if (p->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->residual) % 16 == 0);
   if (p->bias_mode == T2H_BIAS_COL) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0);
   P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
-  if (swap) P.epi_mode = EPI_TMA_F32;
+  if (swap) P.epi_mode = swap_direct ? EPI_DIRECT : EPI_TMA_F32;
   if (p->gn_stats && !swap) {
     T2H_CHECK_ARG(P.epi_mode == EPI_TMA_F32, "tapgemm: gn_stats needs an aligned fp32 NHWC output");
     T2H_CHECK_ARG(p->gn_cpg >= 2 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0,

@@ -52,7 +52,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmD);
+    if (P.epi_mode != EPI_DIRECT) tma_prefetch_desc(&tmD);
     if (P.residual) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
@@ -242,7 +242,8 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
       const int c0 = t.n0 + q * 32;  // this warp's first output channel
-      const float bias_c = (P.bias_mode == T2H_BIAS_COL) ? __ldg(P.bias + c0 + lane) : 0.f;
+      const float bias_c =
+          (P.bias_mode == T2H_BIAS_COL && c0 + lane < P.n_out) ? __ldg(P.bias + c0 + lane) : 0.f;
       auto issue_res = [&](int k) {
         mbar_expect_tx(&res_bar[e], kWarpTile);
         tma_load_4d(&tmR, &res_bar[e], my_res, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
@@ -306,6 +307,20 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               gss = fmaf(x, x, gss);
             }
           }
+        }
+        if (P.epi_mode == EPI_DIRECT) {
+          // strided destination (NCHW conv_out, Cout < 128): the few valid channels store their pixels
+          const int c = c0 + lane;
+          if (c < P.n_out) {
+            float* dst = reinterpret_cast<float*>(P.d) + (long long)t.img * P.d_sn + (long long)c * P.d_sc;
+            const int hrow0 = t.h0 + k * rows_per_chunk;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int h = hrow0 + (i >> tw_shift), w = t.w0 + (i & (P.TW - 1));
+              if (h < P.H && w < P.W) dst[(long long)h * P.d_sh + (long long)w * P.d_sw] = v[i];
+            }
+          }
+          continue;
         }
         if (lane == 0) tma_store_wait_read<0>();  // my_out's previous store has drained
         __syncwarp();
