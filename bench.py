@@ -188,7 +188,7 @@ def side_workloads(dev, precision):
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (PyTorch fp32, oracle port), rank 0 only."""
     if rank != 0:
-        return
+        return None
     threads = host_threads()
     from oracle import vqgan_ref
     import golden_recipes as R
@@ -218,10 +218,38 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=value, unit="img/s", cores=threads, kind="port",
                                   sample=f"{args.steps} steps x 1 image 512x256, torch fp32, {threads} threads"),
                 e2e=dict(value=value, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    return line
+
+
+class StdoutToStderr:
+    """Everything libraries print while the benchmark runs (NCCL's version banner, the Decoder's z-shape
+    line, ...) goes to stderr at the file-descriptor level; stdout carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def emit(line):
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
 
 
 def main():
+    with StdoutToStderr():
+        line = run()
+    if line is not None:
+        emit(line)
+
+
+def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -242,8 +270,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+        return run_reference(args, rank, world)
 
     import torch.distributed as dist
     from text2human_b200 import _lib, ops
@@ -369,6 +396,7 @@ def main():
     if world > 1:
         dist.barrier()
 
+    line = None
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -393,9 +421,9 @@ def main():
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, extra=extra,
                     pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
                     pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -215,6 +215,11 @@ int t2h_vq_gather(const float* codebook, const int64_t* idx, const int32_t* book
                   int b, int hz, int wz, int cz, int ps, int n_books, int n_e,
                   float* zq_nhwc, float* zq_nchw, t2h_stream_t stream);
 
+/* segmentation ids [B,1,H,W] (float) -> one-hot fp16 planes NHWC [terms][B][H][W][c_pad]: the input of the
+ * segm tokeniser's Encoder; replaces F.one_hot(...).permute(0,3,1,2).float() (sample_model.py:331-335) */
+int t2h_onehot_to_planes(const float* ids, void* out, int b, int h, int w, int n_classes, int c_pad, int terms,
+                         t2h_stream_t stream);
+
 /* nearest-neighbour resize of a float id map [B,1,Hs,Ws] to int32 [B,Ht,Wt]
  * (F.interpolate(mode='nearest'), vqgan_arch.py:222,:385-389) */
 int t2h_mask_to_ids(const float* mask, int32_t* ids, int b, int hs, int ws, int ht,

@@ -234,3 +234,57 @@ def test_fused_groupnorm_statistics_in_conv_epilogue(cuda, C, Cout, H, W):
     o1, s1 = ops.conv1x1(a, ops.pack_linear_weight(w[:, :, 1, 1].contiguous(), 2), b, want_stats=True)
     o1d = o1.double().view(3, H * W, 32, Cout // 32)
     assert _rel(s1, torch.stack((o1d.sum((1, 3)), (o1d * o1d).sum((1, 3))), -1)) < 1e-5
+
+
+@pytest.mark.parametrize("terms", [1, 2])
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(1, 37, 19, 40, 128), (2, 21, 50, 128, 256), (1, 5, 3, 64, 128),
+                                            (3, 33, 17, 72, 72), (1, 512, 256, 8, 128)])
+def test_conv3x3_ragged_shapes_with_residual_and_stats(cuda, terms, N, H, W, Cin, Cout):
+    """image extents that are not multiples of the 16x8 / 16x16 pixel tiles, channel counts that are not
+    multiples of the 64-wide K chunk: TMA clipping on loads and stores, partial-tile GroupNorm sums"""
+    from text2human_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(N * H + W + Cin)
+    x = torch.randn(N, Cin, H, W, device=cuda, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda, generator=g) / (9 * Cin) ** 0.5
+    b = torch.randn(Cout, device=cuda, generator=g)
+    res = torch.randn(N, H, W, Cout, device=cuda, generator=g)
+    a = ops.nchw_to_planes(x, terms=terms)
+    wp = ops.pack_conv_weight(w, terms, c_pad=a.shape[-1])
+    out, stats = ops.conv3x3(a, wp, b, residual=res, want_stats=True)
+    xe = _sum(a)[..., :Cin].permute(0, 3, 1, 2).double()
+    we = _sum(wp)[..., :Cin].reshape(3, 3, Cout, Cin).permute(2, 3, 0, 1).double()
+    ref = F.conv2d(xe, we, b.double(), padding=1) + res.permute(0, 3, 1, 2).double()
+    assert _rel(out.permute(0, 3, 1, 2), ref) < 3e-5
+    if Cout % 32 == 0 and (Cout // 32) & (Cout // 32 - 1) == 0 and Cout // 32 >= 2:
+        o = out.double().view(N, H * W, 32, Cout // 32)
+        assert _rel(stats, torch.stack((o.sum((1, 3)), (o * o).sum((1, 3))), -1)) < 1e-5
+    else:
+        assert stats is None
+
+
+def test_upsample_fold_matches_interpolate_then_conv(cuda):
+    from text2human_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(77)
+    for (N, H, W, C) in [(2, 16, 8, 128), (1, 9, 5, 64), (1, 32, 16, 256)]:
+        x = torch.randn(N, H, W, C, device=cuda, generator=g)
+        w = torch.randn(C, C, 3, 3, device=cuda, generator=g) / (9 * C) ** 0.5
+        b = torch.randn(C, device=cuda, generator=g)
+        out, stats = ops.upsample_conv3x3(ops.f32_to_planes(x, ops.CVT_PLAIN, 2), ops.pack_upsample_conv_weight(w, 2), b,
+                                          want_stats=True)
+        ref = F.conv2d(F.interpolate(x.permute(0, 3, 1, 2).double(), scale_factor=2.0, mode="nearest"), w.double(),
+                       b.double(), padding=1)
+        assert out.shape == (N, 2 * H, 2 * W, C)
+        assert _rel(out.permute(0, 3, 1, 2), ref) < 3e-5
+        o = out.double().view(N, 4 * H * W, 32, C // 32)
+        assert _rel(stats, torch.stack((o.sum((1, 3)), (o * o).sum((1, 3))), -1)) < 1e-5
+
+
+def test_tapgemm_rejects_inconsistent_requests(cuda):
+    from text2human_b200 import _lib, ops
+    a = ops.split_planes(torch.randn(64, 64, device=cuda), 1)
+    w = ops.pack_linear_weight(torch.randn(32, 64, device=cuda), 2)
+    out = ops.linear(a, w)  # mixed plane counts fall back to one product and still work
+    assert out.shape == (64, 32)
+    bad = ops.split_planes(torch.randn(64, 60, device=cuda), 1)[:, :, :57]  # row stride 60 halves: not 16-byte aligned
+    with pytest.raises(_lib.T2HError):
+        ops.linear(bad, ops.pack_linear_weight(torch.randn(32, 57, device=cuda), 1))

@@ -249,3 +249,64 @@ def test_sampler_transformer_logits_and_sampling_loop(cuda, mode):
         assert ((x_t // 1024) == texm).all(), "tokens must come from the position's own texture codebook"
         for k in range(18):
             assert ((out[k] >= 0) == (texm == k)).all() and out[k].max() < 1024
+
+
+SEGM_OPT = dict(segm_double_z=False, segm_z_channels=32, segm_resolution=512, segm_in_channels=24, segm_out_ch=24,
+                segm_ch=64, segm_ch_mult=[1, 1, 2, 2, 4], segm_num_res_blocks=1, segm_attn_resolutions=[16],
+                segm_dropout=0.0, segm_num_segm_classes=24, segm_n_embed=1024, segm_embed_dim=32)
+
+
+def test_segm_tokenizer_matches_oracle(cuda):
+    """get_quantized_segm (sample_model.py:330-340): one-hot(24) -> segm Encoder (ch 64, 2 channels per
+    GroupNorm group) -> 1x1 -> VectorQuantizer(1024, 32) on a 128x64 parsing map."""
+    from oracle import vqgan_ref
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import SegmTokenizer
+    ops.set_precision("fp32")
+    torch.manual_seed(21)
+    m = SegmTokenizer(SEGM_OPT)
+    m.segm_quantizer.embedding.weight.data.copy_(R.codebooks(5, 1, 1024, 32, "trained")[0])
+    m = m.to(cuda).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    segm = R.blocky_mask(6, 2, 128, 64, 8, n_ids=24).to(cuda)
+    tokens = m.get_quantized_segm(segm)
+    assert tokens.shape == (2, 8, 4) and tokens.dtype == torch.int64
+    with torch.no_grad():
+        oh = torch.nn.functional.one_hot(segm.squeeze(1).long(), 24).permute(0, 3, 1, 2).float()
+        z = vqgan_ref.conv(sd, "segm_quant_conv", vqgan_ref.encoder(sd, oh, "segm_encoder."), padding=0)
+        _, _, want = vqgan_ref.quantize_plain(sd["segm_quantizer.embedding.weight"], z)
+    a = ops.onehot_to_planes(segm, 24)
+    assert torch.equal(a.float().sum(0).permute(0, 3, 1, 2), oh)
+    zz = m.segm_encoder.forward_planes(a)
+    assert _rel(zz.permute(0, 3, 1, 2), vqgan_ref.encoder(sd, oh, "segm_encoder.")) < TOL_EXACT
+    assert (tokens == want).float().mean().item() >= 0.95
+
+
+def test_decode_from_indices_matches_oracle(cuda):
+    """tokens -> image (the decode half of sample_and_refine, sample_model.py:225-243), batched"""
+    from oracle import vqgan_ref
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import HierarchyVQSpatialTextureAwareModel
+    ops.set_precision("fp32")
+    torch.manual_seed(9)
+    m = HierarchyVQSpatialTextureAwareModel(HIER_OPT).to(cuda).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cbt = torch.stack([e.weight.detach() for e in m.top_quantize.embedding_list])
+    cbb = torch.stack([e.weight.detach() for e in m.bot_quantize.embedding_list])
+    B = 2
+    mask = R.blocky_mask(12, B, 512, 256, 64).to(cuda)
+    tex = torch.nn.functional.interpolate(mask, (32, 16), mode="nearest")[:, 0].long()
+    g = torch.Generator().manual_seed(1)
+    top = torch.randint(0, 1024, (B, 32, 16), generator=g).to(cuda)
+    bot = torch.randint(0, 512, (B, 32, 16), generator=g).to(cuda)
+    top_list = [torch.where(tex == k, top, torch.full_like(top, -1)) for k in range(18)]
+    bot_list = [torch.where(tex == k, bot, torch.full_like(bot, -1)) for k in range(18)]
+    dec = m.decode_from_indices(top_list, bot_list, mask)
+    with torch.no_grad():
+        qt = vqgan_ref.codebook_entry_texture(cbt, top_list, mask, (B, 32, 16, 256))
+        qt = vqgan_ref.conv(sd, "top_post_quant_conv", qt, padding=0)
+        qb = vqgan_ref.codebook_entry_texture(cbb, bot_list, mask, (B, 32, 16, 256), ps=2)
+        res = vqgan_ref.decoder_res(sd, vqgan_ref.conv(sd, "bot_post_quant_conv", qb, padding=0), "bot_decoder_res.")
+        want = vqgan_ref.decoder(sd, qt, "decoder.", bot_h=res)
+    assert dec.shape == (B, 3, 512, 256)
+    assert _rel(dec, want) < TOL_EXACT

@@ -64,6 +64,7 @@ SIGNATURES = {
     "t2h_vq_workspace_bytes": (_L, [_L, _I, _I]),
     "t2h_vq_gather": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "t2h_mask_to_ids": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "t2h_onehot_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "t2h_embed_sum": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "t2h_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
 }

@@ -355,6 +355,29 @@ __global__ void mask_to_ids_kernel(const float* __restrict__ mask, int* __restri
   }
 }
 
+// ids [B][HW] (float class ids) -> one-hot fp16 planes [terms][B][HW][c_pad]; the lo plane of an exact
+// 0/1 value is zero.  Replaces F.one_hot(...).permute(0,3,1,2).float() (sample_model.py:331-335).
+__global__ void onehot_to_planes_kernel(const float* __restrict__ ids, __half* __restrict__ out, long long npix,
+                                        int c_pad, int n_classes, int terms, long long plane) {
+  const int c8 = c_pad >> 3;
+  const long long total = npix * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / c8;
+    const int c0 = (int)(i % c8) * 8;
+    const float v = ids[p];
+    const int cls = (v == floorf(v) && v >= 0.f && v < (float)n_classes) ? (int)v : -1;
+    Half8 hi, lo;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi.v[e] = __float2half_rn((c0 + e) == cls ? 1.f : 0.f);
+      lo.v[e] = __float2half_rn(0.f);
+    }
+    *reinterpret_cast<Half8*>(out + i * 8) = hi;
+    if (terms == 2) *reinterpret_cast<Half8*>(out + plane + i * 8) = lo;
+  }
+}
+
 static inline int grid_for(long long work, int block) {
   long long g = ceil_div64(work, block);
   long long cap = (long long)num_sms() * 16;
@@ -510,6 +533,18 @@ int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex, c
   embed_sum_kernel<<<b * t, 128, 0, as_stream(stream)>>>(
       reinterpret_cast<const long long*>(idx), reinterpret_cast<const long long*>(segm),
       reinterpret_cast<const long long*>(tex), tok_emb, pos_emb, segm_emb, tex_emb, x, t, c);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_onehot_to_planes(const float* ids, void* out, int b, int h, int w, int n_classes, int c_pad, int terms,
+                         t2h_stream_t stream) {
+  T2H_CHECK_ARG(ids && out && b > 0 && h > 0 && w > 0 && n_classes > 0, "onehot_to_planes: bad args");
+  T2H_CHECK_ARG(c_pad >= n_classes && c_pad % 8 == 0, "onehot_to_planes: c_pad=%d", c_pad);
+  T2H_CHECK_ARG(terms == 1 || terms == 2, "onehot_to_planes: terms=%d", terms);
+  const long long npix = (long long)b * h * w;
+  onehot_to_planes_kernel<<<grid_for(npix * (c_pad / 8), 256), 256, 0, as_stream(stream)>>>(
+      ids, reinterpret_cast<__half*>(out), npix, c_pad, n_classes, terms, npix * c_pad);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -491,6 +491,19 @@ def embed_sum(idx, segm, tex, tok_emb, pos_emb, segm_emb, tex_emb):
     return x
 
 
+def onehot_to_planes(segm, n_classes, terms=None):
+    """float class-id map [B,1,H,W] -> one-hot planes [T,B,H,W,c_pad]"""
+    _need_cuda(segm)
+    segm = _f32c(segm)
+    B, _, H, W = segm.shape
+    terms = terms or get_terms()
+    cp = (n_classes + 7) // 8 * 8
+    out = torch.empty((terms, B, H, W, cp), dtype=torch.float16, device=segm.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_onehot_to_planes(_ptr(segm), _ptr(out), B, H, W, n_classes, cp, terms, _stream()))
+    return out
+
+
 def mask_to_ids(mask, ht, wt):
     """float id map [B,1,Hs,Ws] -> int32 [B,ht,wt] (nearest)."""
     _need_cuda(mask)

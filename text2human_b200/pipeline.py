@@ -154,6 +154,31 @@ class HierarchyVQSpatialTextureAwareModel(nn.Module):
         return self.decoder.forward_nhwc(quant_top, bot_h=res)
 
 
+class SegmTokenizer(nn.Module):
+    """parsing map -> 32x16 segmentation tokens: one-hot -> segm Encoder -> 1x1 -> VectorQuantizer
+    (BaseSampleModel.get_quantized_segm, sample_model.py:330-340; constructor keys as the segm_* entries of
+    configs/sample_from_parsing.yml)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.segm_encoder = Encoder(ch=opt['segm_ch'], num_res_blocks=opt['segm_num_res_blocks'],
+                                    attn_resolutions=opt['segm_attn_resolutions'], ch_mult=opt['segm_ch_mult'],
+                                    in_channels=opt['segm_in_channels'], resolution=opt['segm_resolution'],
+                                    z_channels=opt['segm_z_channels'], double_z=opt['segm_double_z'],
+                                    dropout=opt['segm_dropout'])
+        self.segm_quantizer = VectorQuantizer(opt['segm_n_embed'], opt['segm_embed_dim'], beta=0.25,
+                                              sane_index_shape=True)
+        self.segm_quant_conv = torch.nn.Conv2d(opt["segm_z_channels"], opt['segm_embed_dim'], 1)
+
+    @torch.no_grad()
+    def get_quantized_segm(self, segm):
+        """segm: [B,1,H,W] class ids -> int64 tokens [B,h,w]"""
+        a = ops.onehot_to_planes(segm, self.opt['segm_num_segm_classes'])
+        z = conv1x1_nhwc(self.segm_encoder.forward_planes(a), self.segm_quant_conv)
+        return self.segm_quantizer.forward_nhwc(z)["idx"]
+
+
 class GraphedStep:
     """Capture a fixed-shape, allocation-stable sequence of libt2h launches into a CUDA graph and replay
     it (CUDA streams + graphs instead of a tracing compiler).  ``fn(*static_inputs) -> tensor | tuple``.

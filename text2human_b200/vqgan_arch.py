@@ -311,6 +311,12 @@ class Encoder(nn.Module):
         return h
 
     @torch.no_grad()
+    def forward_planes(self, a):
+        """fp16 planes NHWC [T,N,H,W,c_pad] in (e.g. a one-hot segmentation), fp32 NHWC latent out."""
+        h = _Act(*ops.conv3x3(a, _conv_w(self.conv_in, a.shape[-1]), _f32(self.conv_in.bias), want_stats=True))
+        return _conv_out(self.norm_out, self.conv_out, self._body(h), nchw=False)
+
+    @torch.no_grad()
     def forward_nhwc(self, x_nchw):
         """fp32 NCHW image in (the network entry is NCHW either way), fp32 NHWC latent out."""
         h = self._body(_conv_in_nchw(self.conv_in, x_nchw))
