@@ -237,6 +237,44 @@ int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex,
 int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* out,
                   int64_t rows, int c, float eps, int terms, t2h_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Training step of the index-prediction transformer
+ * (TransformerTextureAwareModel._train_loss / optimize_parameters, models/transformer_model.py:232-303;
+ *  loss.backward() + torch.optim.Adam.step()).  Dense gradients (dgrad / wgrad / attention) run on
+ * t2h_tapgemm; these are the HBM-bound pieces around it.
+ * ---------------------------------------------------------------------- */
+/* fp32 [g][r][c] -> fp16 planes transposed out_t[terms][g][c][r] (+ untransposed out_n, may be NULL):
+ * wgrad contracts over rows, so both operands are needed row-contiguous */
+int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms,
+                        t2h_stream_t stream);
+/* fp16 planes [terms][g][r][c] (row stride ld, group stride g_stride, plane stride in_plane, elements)
+ * -> [terms][g][c][r] with output row stride out_ld, group stride out_g_stride, plane stride out_plane */
+int t2h_planes_transpose(const void* x, void* out, int g, int r, int c, int64_t ld, int64_t g_stride,
+                         int64_t in_plane, int64_t out_ld, int64_t out_g_stride, int64_t out_plane, int terms,
+                         t2h_stream_t stream);
+/* out[c] += sum_r x[r][c]   (bias gradients) */
+int t2h_colsum(const float* x, float* out, int64_t rows, int c, t2h_stream_t stream);
+/* exact-erf GELU forward to fp16 planes, and backward da = dg * gelu'(a) (nn.GELU, transformer_arch.py:86) */
+int t2h_gelu_fwd(const float* a, void* out, int64_t n, int terms, t2h_stream_t stream);
+int t2h_gelu_bwd(const float* a, const float* dg, float* da, int64_t n, t2h_stream_t stream);
+/* LayerNorm backward; dx is overwritten or (accumulate=1) added to; dgamma/dbeta are accumulated */
+int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                      float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream);
+/* ds = scale * p * (dp - sum_j dp_j p_j) over the last dim; p as fp16 planes */
+int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
+                    t2h_stream_t stream);
+/* masked multi-head cross-entropy: row m belongs to head[m], target[m] (-1 = ignored), weight w[m]:
+ * loss_rows[m] = CE (unweighted), dlogits [rows][nh][ncls] = w*(softmax - onehot) in the own head, 0 elsewhere
+ * (F.cross_entropy(ignore_index=-1) over 18 heads, transformer_model.py:250-256) */
+int t2h_ce_heads(const float* logits, const int64_t* target, const int64_t* head, const float* w,
+                 float* loss_rows, float* dlogits, int64_t rows, int nh, int ncls, t2h_stream_t stream);
+/* de[idx[m]] += dx[m] (idx NULL: row index m % t_mod, the positional table) */
+int t2h_embed_bwd(const float* dx, const int64_t* idx, float* de, int64_t rows, int c, int t_mod,
+                  t2h_stream_t stream);
+/* torch.optim.Adam step (weight_decay 0); g is multiplied by grad_scale first (1/world after a sum all-reduce) */
+int t2h_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, int step, float grad_scale, t2h_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,3 +95,39 @@ def sample_fn(logits_fn, segm_tokens, texture_mask, latent_shape, mask_id, sampl
                 out[k][sel] = draw[sel]
         x_t = flat.view(B, n)
     return [o.view(B, n) for o in out], x_t
+
+
+def train_loss(sd, x_0, gt_list, segm_tokens, texture_tokens, t, mask, n_head, mask_id, num_timesteps=1000,
+               loss_type="reweighted_elbo"):
+    """TransformerTextureAwareModel._train_loss (transformer_model.py:232-271) with the random draws
+    (t from sample_time :198-207, the mask from q_sample :212-230) passed in so that it is a pure function.
+    x_0 [B,T] continual tokens; gt_list: per-texture ground-truth indices with -1 outside the texture.
+    -> (loss, vb_loss) scalars with autograd history back to ``sd``."""
+    x_t = x_0.clone()
+    x_t[mask] = mask_id
+    logits_list = transformer_logits(sd, x_t, segm_tokens, texture_tokens, n_head)
+    ce = 0
+    for lg, gt in zip(logits_list, gt_list):
+        gt_ignore = gt.clone()
+        gt_ignore[~mask] = -1
+        ce = ce + F.cross_entropy(lg.permute(0, 2, 1), gt_ignore, ignore_index=-1, reduction="none").sum(1)
+    pt = torch.ones_like(t).float() / num_timesteps
+    ntok = x_0.shape[1:].numel()
+    vb = ce / t / pt / (math.log(2) * ntok)
+    if loss_type == "elbo":
+        loss = vb
+    elif loss_type == "reweighted_elbo":
+        loss = (1 - (t / num_timesteps)) * ce / (math.log(2) * ntok)
+    else:
+        raise ValueError(loss_type)
+    return loss.mean(), vb.mean()
+
+
+def adam_update(p, g, m, v, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    """one torch.optim.Adam step (weight_decay 0, amsgrad off) restated; returns new (p, m, v)"""
+    m = betas[0] * m + (1 - betas[0]) * g
+    v = betas[1] * v + (1 - betas[1]) * g * g
+    bc1 = 1 - betas[0] ** step
+    bc2 = 1 - betas[1] ** step
+    p = p - (lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps)
+    return p, m, v

@@ -89,3 +89,18 @@ TINY_DECRES = dict(in_channels=3, resolution=32, z_channels=32, ch=32, num_res_b
 TINY_TRANSFORMER = dict(codebook_size=18 * 16, segm_codebook_size=32, texture_codebook_size=18, bert_n_emb=64,
                         bert_n_layers=2, bert_n_head=4, block_size=32, latent_shape=[8, 4], embd_pdrop=0.0,
                         resid_pdrop=0.0, attn_pdrop=0.0, num_head=18)
+
+
+def sampler_train_batch(seed, B=2, cfg=None):
+    """deterministic training batch for the index-prediction transformer: continual tokens x_0, the 18
+    per-texture ground-truth lists (-1 outside the texture), segm and texture tokens"""
+    cfg = cfg or TINY_TRANSFORMER
+    T = cfg["block_size"]
+    ncls = cfg["codebook_size"] // cfg["num_head"]
+    g = _gen(seed, "train_batch")
+    tex = torch.randint(0, cfg["num_head"], (B, T), generator=g)
+    own = torch.randint(0, ncls, (B, T), generator=g)
+    segm = torch.randint(0, cfg["segm_codebook_size"], (B, T), generator=g)
+    x_0 = own + ncls * tex
+    gt_list = [torch.where(tex == k, own, torch.full_like(own, -1)) for k in range(cfg["num_head"])]
+    return x_0, gt_list, segm, tex

@@ -62,3 +62,47 @@ def test_shard_range_covers_everything_once():
                 assert 0 <= a <= b <= n
                 seen += list(range(a, b))
             assert seen == list(range(n))
+
+
+def _train_worker(rank, world, port, q):
+    """the trainer's bucketed gradient all-reduce (host logic) on CPU tensors over gloo"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import golden_recipes as R
+    from text2human_b200.transformer_arch import TransformerMultiHead
+    from text2human_b200.transformer_train import SamplerTrainer
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    D.init("gloo")
+    cfg = dict(R.TINY_TRANSFORMER, bert_n_layers=5)
+    tr = SamplerTrainer(TransformerMultiHead(**cfg), bucket_layers=2)
+    n = tr.flat_g.numel()
+    tr.flat_g.copy_(torch.arange(n, dtype=torch.float32) % 97 + 1000.0 * rank)
+    # the order the backward pass finishes the buckets in: head, blocks last to first, embeddings
+    tr._bucket_done("head", True)
+    for li in range(4, -1, -1):
+        if li % tr.bucket_layers == 0:
+            tr._bucket_done((li, min(5, li + tr.bucket_layers)), True)
+    tr._bucket_done("emb", True)
+    n_handles = len(tr._handles)
+    tr.wait_reduced()
+    if rank == 0:
+        q.put((tr.flat_g.clone(), n_handles))
+    torch.distributed.destroy_process_group()
+
+
+def test_trainer_gradient_buckets_cover_flat_buffer_gloo():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g, n_handles = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    n = g.numel()
+    want = 2 * (torch.arange(n, dtype=torch.float32) % 97) + 1000.0   # every element summed exactly once
+    assert torch.equal(g, want)
+    assert n_handles == 1 + 3 + 1                                     # head, 3 block buckets, embeddings

@@ -1,0 +1,410 @@
+// Backward / optimiser kernels of the index-prediction transformer's training step
+// (TransformerTextureAwareModel._train_loss / optimize_parameters, models/transformer_model.py:232-303).
+// Every dense contraction of the backward pass (dgrad, wgrad, attention gradients) runs on the same
+// tcgen05 tap-GEMM as the forward pass; this file holds the HBM-bound pieces around them: operand
+// transposes (wgrad contracts over rows, so both operands are needed row-contiguous), GELU / LayerNorm /
+// softmax backward, the masked multi-head cross-entropy, embedding scatter-add, column sums (bias
+// gradients) and Adam.
+#include "t2h_internal.h"
+#include "t2h_ptx.cuh"
+
+namespace t2h {
+
+// fp32 [G][R][C] -> fp16 planes, transposed: out[t][g][c][r]   (and optionally the untransposed planes)
+__global__ void f32_to_planes_t_kernel(const float* __restrict__ x, __half* __restrict__ out_t,
+                                       __half* __restrict__ out_n, int R, int C, int terms, long long plane) {
+  __shared__ float tile[32][33];
+  const int g = blockIdx.z;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xg = x + (long long)g * R * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    const float v = (r < R && c < C) ? xg[(long long)r * C + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (out_n && r < R && c < C) {
+      __half hi, lo;
+      split_f16(v, hi, lo);
+      const long long o = (long long)g * R * C + (long long)r * C + c;
+      out_n[o] = hi;
+      if (terms == 2) out_n[plane + o] = lo;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) {
+      __half hi, lo;
+      split_f16(tile[threadIdx.x][i], hi, lo);
+      const long long o = (long long)g * R * C + (long long)c * R + r;
+      out_t[o] = hi;
+      if (terms == 2) out_t[plane + o] = lo;
+    }
+  }
+}
+
+// fp16 planes [T][G][R][C] (row stride ld, column offset applied by the caller) -> [T][G][C][R]
+__global__ void planes_transpose_kernel(const __half* __restrict__ x, __half* __restrict__ out, int R, int C,
+                                        long long ld, long long g_stride, long long in_plane, int terms,
+                                        long long out_ld, long long out_g_stride, long long out_plane) {
+  __shared__ __half tile[2][32][34];
+  const int g = blockIdx.z;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int t = 0; t < terms; ++t) {
+    const __half* xg = x + t * in_plane + (long long)g * g_stride;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      tile[t][i][threadIdx.x] = (r < R && c < C) ? xg[(long long)r * ld + c] : __float2half(0.f);
+    }
+  }
+  __syncthreads();
+  for (int t = 0; t < terms; ++t)
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) out[t * out_plane + (long long)g * out_g_stride + (long long)c * out_ld + r] = tile[t][threadIdx.x][i];
+    }
+}
+
+// out[c] += sum_r x[r][c]
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long R, int C,
+                              int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += x[r * C + c];
+  atomicAdd(&out[c], s);
+}
+
+// exact-erf GELU: g = gelu(a) -> planes;  backward: da = dg * gelu'(a)
+__global__ void gelu_fwd_kernel(const float* __restrict__ a, __half* __restrict__ out, long long n, int terms,
+                                long long plane) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    __half hi, lo;
+    split_f16(gelu_erf(a[i]), hi, lo);
+    out[i] = hi;
+    if (terms == 2) out[plane + i] = lo;
+  }
+}
+__global__ void gelu_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dg,
+                                float* __restrict__ da, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float x = a[i];
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    da[i] = dg[i] * (cdf + x * pdf);
+  }
+}
+
+// LayerNorm backward, one warp per row (C <= 1024): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma;
+// dx (+)= into dx_out (accumulate flag), dgamma += dy*xhat, dbeta += dy (atomics)
+template <int PER_LANE>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ gamma, float* __restrict__ dx,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
+                                     float eps, int accumulate) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  float dg_acc[PER_LANE], db_acc[PER_LANE], gam[PER_LANE];
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    dg_acc[i] = 0.f;
+    db_acc[i] = 0.f;
+    gam[i] = c < C ? gamma[c] : 0.f;
+  }
+  // each warp walks rows with a grid stride and keeps its dgamma/dbeta partial sums in registers
+  for (long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * warps) {
+    const float* xr = x + row * C;
+    const float* dyr = dy + row * C;
+    float xv[PER_LANE], gv[PER_LANE];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      xv[i] = c < C ? xr[c] : 0.f;
+      sum += xv[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      const float d = c < C ? xv[i] - mean : 0.f;
+      sq += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / C + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) {
+        const float xhat = (xv[i] - mean) * rstd;
+        const float d = dyr[c];
+        xv[i] = xhat;
+        gv[i] = d * gam[i];
+        s1 += gv[i];
+        s2 += gv[i] * xhat;
+        dg_acc[i] += d * xhat;
+        db_acc[i] += d;
+      } else {
+        gv[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 / C, m2 = s2 / C;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+      const int c = lane + i * 32;
+      if (c < C) {
+        const float v = rstd * (gv[i] - m1 - xv[i] * m2);
+        dx[row * C + c] = accumulate ? dx[row * C + c] + v : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      atomicAdd(&dgamma[c], dg_acc[i]);
+      atomicAdd(&dbeta[c], db_acc[i]);
+    }
+  }
+}
+
+// softmax backward over the last dim: ds = scale * p * (dp - sum_j dp_j p_j); p given as fp16 planes
+template <int PER_LANE>
+__global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __restrict__ dp,
+                                   float* __restrict__ ds, long long rows, int cols, float scale, int terms,
+                                   long long plane) {
+  const int warps = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float pv[PER_LANE], dv[PER_LANE];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < cols) {
+      float v = __half2float(p[row * cols + c]);
+      if (terms == 2) v += __half2float(p[plane + row * cols + c]);
+      pv[i] = v;
+      dv[i] = dp[row * cols + c];
+      dot += v * dv[i];
+    } else {
+      pv[i] = 0.f;
+      dv[i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < cols) ds[row * cols + c] = scale * pv[i] * (dv[i] - dot);
+  }
+}
+
+// Masked multi-head cross-entropy (transformer_model.py:250-270): row m belongs to head head[m]; its target
+// is target[m] (-1 = not masked = ignored).  loss_rows[m] = CE (unweighted), dlogits = w[m] * (softmax - onehot)
+// inside the row's own head, 0 in every other head.  One block per row.
+__global__ void ce_heads_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                const long long* __restrict__ head, const float* __restrict__ w,
+                                float* __restrict__ loss_rows, float* __restrict__ dlogits, int nh, int ncls) {
+  const long long m = blockIdx.x;
+  const int tid = threadIdx.x;
+  const long long tgt = target[m];
+  const int hd = (int)head[m];
+  float* drow = dlogits + m * (long long)nh * ncls;
+  for (int i = tid; i < nh * ncls; i += blockDim.x) drow[i] = 0.f;
+  if (tgt < 0 || hd < 0 || hd >= nh) {
+    if (tid == 0) loss_rows[m] = 0.f;
+    return;
+  }
+  __shared__ float red[32];
+  const float* lr = logits + m * (long long)nh * ncls + (long long)hd * ncls;
+  float mx = -INFINITY;
+  for (int i = tid; i < ncls; i += blockDim.x) mx = fmaxf(mx, lr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = tid; i < ncls; i += blockDim.x) sum += expf(lr[i] - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) red[tid >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) sum += red[i];
+  const float lse = mx + logf(sum);
+  const float wm = w[m];
+  __syncthreads();  // drow zero-fill above must be complete before the own-head slice is overwritten
+  for (int i = tid; i < ncls; i += blockDim.x)
+    drow[(long long)hd * ncls + i] = wm * (expf(lr[i] - lse) - (i == tgt ? 1.f : 0.f));
+  if (tid == 0) loss_rows[m] = lse - lr[tgt];  // unweighted; the caller forms loss and vb_loss from it
+}
+
+// dE[idx[m]] += dx[m]  (embedding backward; also the positional table with idx = m % T)
+__global__ void embed_bwd_kernel(const float* __restrict__ dx, const long long* __restrict__ idx,
+                                 float* __restrict__ dE, long long rows, int C, int T_mod) {
+  const long long m = blockIdx.x;
+  if (m >= rows) return;
+  const long long e = idx ? idx[m] : (m % T_mod);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dE[e * C + c], dx[m * C + c]);
+}
+
+// torch.optim.Adam (weight_decay 0, amsgrad off), fp32
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+static inline int grid1d(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace t2h
+
+using namespace t2h;
+
+extern "C" {
+
+int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms,
+                        t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && out_t && g > 0 && r > 0 && c > 0, "f32_to_planes_t: bad args");
+  T2H_CHECK_ARG(terms == 1 || terms == 2, "f32_to_planes_t: terms=%d", terms);
+  dim3 grid(ceil_div(r, 32), ceil_div(c, 32), g), block(32, 8);
+  f32_to_planes_t_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<__half*>(out_t), reinterpret_cast<__half*>(out_n), r, c, terms, (long long)g * r * c);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_planes_transpose(const void* x, void* out, int g, int r, int c, int64_t ld, int64_t g_stride,
+                         int64_t in_plane, int64_t out_ld, int64_t out_g_stride, int64_t out_plane, int terms,
+                         t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && out && g > 0 && r > 0 && c > 0 && ld >= c && out_ld >= r, "planes_transpose: bad args");
+  T2H_CHECK_ARG(terms == 1 || terms == 2, "planes_transpose: terms=%d", terms);
+  dim3 grid(ceil_div(r, 32), ceil_div(c, 32), g), block(32, 8);
+  planes_transpose_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), r, c, ld, g_stride, in_plane, terms,
+      out_ld, out_g_stride, out_plane);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_colsum(const float* x, float* out, int64_t rows, int c, t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && out && rows > 0 && c > 0, "colsum: bad args");
+  const int rpb = 64;
+  dim3 grid(ceil_div(c, 128), (unsigned)ceil_div64(rows, rpb));
+  colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, out, rows, c, rpb);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_gelu_fwd(const float* a, void* out, int64_t n, int terms, t2h_stream_t stream) {
+  T2H_CHECK_ARG(a && out && n > 0 && (terms == 1 || terms == 2), "gelu_fwd: bad args");
+  gelu_fwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(a, reinterpret_cast<__half*>(out), n, terms, n);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_gelu_bwd(const float* a, const float* dg, float* da, int64_t n, t2h_stream_t stream) {
+  T2H_CHECK_ARG(a && dg && da && n > 0, "gelu_bwd: bad args");
+  gelu_bwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(a, dg, da, n);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                      float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream) {
+  T2H_CHECK_ARG(dy && x && gamma && dx && dgamma && dbeta && rows > 0 && c > 0, "layernorm_bwd: bad args");
+  T2H_CHECK_ARG(c <= 1024, "layernorm_bwd: C=%d > 1024 unsupported", c);
+  const int warps = 4;
+  long long want = ceil_div64(rows, warps * 8);  // ~8 rows per warp: 8x fewer dgamma/dbeta atomics
+  const int grid = (int)(want < 1 ? 1 : want);
+  cudaStream_t st = as_stream(stream);
+  if (c <= 512)
+    layernorm_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate);
+  else
+    layernorm_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
+                    t2h_stream_t stream) {
+  T2H_CHECK_ARG(p && dp && ds && rows > 0 && cols > 0 && cols <= 2048, "softmax_bwd: bad args");
+  T2H_CHECK_ARG(terms == 1 || terms == 2, "softmax_bwd: terms=%d", terms);
+  const int warps = 4;
+  const int grid = (int)ceil_div64(rows, warps);
+  cudaStream_t st = as_stream(stream);
+  const __half* ph = reinterpret_cast<const __half*>(p);
+  if (cols <= 512)
+    softmax_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+  else
+    softmax_bwd_kernel<64><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_ce_heads(const float* logits, const int64_t* target, const int64_t* head, const float* w,
+                 float* loss_rows, float* dlogits, int64_t rows, int nh, int ncls, t2h_stream_t stream) {
+  T2H_CHECK_ARG(logits && target && head && w && loss_rows && dlogits && rows > 0 && nh > 0 && ncls > 0,
+                "ce_heads: bad args");
+  ce_heads_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(
+      logits, reinterpret_cast<const long long*>(target), reinterpret_cast<const long long*>(head), w, loss_rows,
+      dlogits, nh, ncls);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_embed_bwd(const float* dx, const int64_t* idx, float* de, int64_t rows, int c, int t_mod,
+                  t2h_stream_t stream) {
+  T2H_CHECK_ARG(dx && de && rows > 0 && c > 0 && (idx || t_mod > 0), "embed_bwd: bad args");
+  embed_bwd_kernel<<<(unsigned)rows, 128, 0, as_stream(stream)>>>(dx, reinterpret_cast<const long long*>(idx), de,
+                                                                rows, c, t_mod);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+             float eps, int step, float grad_scale, t2h_stream_t stream) {
+  T2H_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adam: bad args");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s,
+                                                            grad_scale);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+}  // extern "C"

@@ -328,23 +328,25 @@ def mha_scores(qk, B, Tn, nh, alpha=1.0):
     return out
 
 
-def mha_pv(p, vt, B, Tn, nh):
+def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True):
     """Multi-head att @ v (transformer_arch.py:65-67).  p: planes [T,B,nh,Tn,Tn];
-    vt: planes [T,B,C,Tn] (v transposed: channels x tokens).  -> planes [T, B*Tn, C] with the
-    heads re-assembled side by side."""
+    vt: planes [T,B,C,Tn] (v transposed: channels x tokens).  -> planes [T, B*Tn, C] (or fp32 [B*Tn, C])
+    with the heads re-assembled side by side.  ``out`` may be a column-sliced view of a wider matrix."""
     _need_cuda(p, vt)
     T = p.shape[0]
     Cc = vt.shape[2]
     hs = Cc // nh
     assert p.is_contiguous() and vt.is_contiguous()
-    out = torch.empty((T, B * Tn, Cc), dtype=torch.float16, device=p.device)
+    if out is None:
+        out = _alloc_out((B * Tn, Cc), planes_out, T, p.device)
+    ld = out.stride(-2)
     _tapgemm(a=p, a_term_imgs=B * nh, a_imgs=T * B * nh, a_bcast=0,
              n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=Tn, a_sw=Tn, a_sh=nh * Tn * Tn, a_sn=Tn * Tn,
              tile_rows=1,
              b=vt, b_term_g=B, b_groups=T * B, b_sg=Cc * Tn, b_batched_h=1,
              b_groups2=nh, b_sg2=hs * Tn, b_batched=1, n_out=hs, b_sn=Tn,
-             taps=_TAPS_1, d=out, d_mode=OUT_PLANES, d_strides=(hs, Tn * Cc, Cc, 1),
-             d_plane=out.stride(0))
+             taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=(hs, Tn * ld, ld, 1),
+             d_plane=out.stride(0) if planes_out else 0)
     return out
 
 
@@ -557,3 +559,110 @@ def vq_gather(codebook, idx, book_id, *, B, Hz, Wz, Cz, ps=1, want_nchw=True, wa
     _lib.check(_lib.load().t2h_vq_gather(_ptr(codebook), _ptr(idx.contiguous()), _ptr(book_id), B, Hz, Wz,
                                          Cz, ps, n_books, n_e, _ptr(zq_nhwc), _ptr(zq_nchw), _stream()))
     return zq_nhwc, zq_nchw
+
+
+# ----------------------------------------------------------------------------
+# training (backward / optimiser) kernels
+# ----------------------------------------------------------------------------
+def f32_to_planes_t(x, terms=None, want_plain=True):
+    """fp32 [G,R,C] (or [R,C]) -> (planes [T,G,R,C] or None, transposed planes [T,G,C,R])"""
+    _need_cuda(x)
+    terms = terms or get_terms()
+    x3 = x if x.dim() == 3 else x.unsqueeze(0)
+    assert x3.is_contiguous() and x3.dtype == torch.float32
+    G, R, Cc = x3.shape
+    out_t = torch.empty((terms, G, Cc, R), dtype=torch.float16, device=x.device)
+    out_n = torch.empty((terms, G, R, Cc), dtype=torch.float16, device=x.device) if want_plain else None
+    _count(1)
+    _lib.check(_lib.load().t2h_f32_to_planes_t(_ptr(x3), _ptr(out_t), _ptr(out_n), G, R, Cc, terms, _stream()))
+    if x.dim() == 2:
+        return (out_n[:, 0] if want_plain else None), out_t[:, 0]
+    return out_n, out_t
+
+
+def planes_transpose(x, out=None):
+    """planes [T,G,R,C] (unit last stride; may be a column-sliced view) -> [T,G,C,R]; ``out`` may be a
+    column-sliced view [T,G,C,R] of a wider tensor (unit last stride)."""
+    _need_cuda(x)
+    T, G, R, Cc = x.shape
+    assert x.stride(3) == 1
+    if out is None:
+        out = torch.empty((T, G, Cc, R), dtype=torch.float16, device=x.device)
+    assert out.shape == (T, G, Cc, R) and out.stride(3) == 1
+    _count(1)
+    _lib.check(_lib.load().t2h_planes_transpose(_ptr(x), _ptr(out), G, R, Cc, x.stride(2), x.stride(1), x.stride(0),
+                                                out.stride(2), out.stride(1), out.stride(0), T, _stream()))
+    return out
+
+
+def colsum_(out, x):
+    """out[c] += sum_r x[r,c] (fp32)"""
+    _need_cuda(x, out)
+    rows, Cc = x.shape
+    assert x.is_contiguous() and out.numel() == Cc
+    _count(1)
+    _lib.check(_lib.load().t2h_colsum(_ptr(x), _ptr(out), rows, Cc, _stream()))
+
+
+def gelu_fwd(a, terms=None):
+    _need_cuda(a)
+    terms = terms or get_terms()
+    out = torch.empty((terms,) + tuple(a.shape), dtype=torch.float16, device=a.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_gelu_fwd(_ptr(a), _ptr(out), a.numel(), terms, _stream()))
+    return out
+
+
+def gelu_bwd(a, dg):
+    _need_cuda(a, dg)
+    da = torch.empty_like(a)
+    _count(1)
+    _lib.check(_lib.load().t2h_gelu_bwd(_ptr(a), _ptr(dg), _ptr(da), a.numel(), _stream()))
+    return da
+
+
+def layernorm_bwd_(dx, dy, x, gamma, dgamma, dbeta, eps=1e-5, accumulate=True):
+    """dx (+)= LayerNorm backward of dy wrt x; dgamma/dbeta accumulated"""
+    _need_cuda(dx, dy, x)
+    rows, Cc = x.shape
+    _count(1)
+    _lib.check(_lib.load().t2h_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+                                             rows, Cc, eps, 1 if accumulate else 0, _stream()))
+
+
+def softmax_bwd(p, dp, scale):
+    """p planes [T, ...rows, cols], dp fp32 [...rows, cols] -> ds fp32"""
+    _need_cuda(p, dp)
+    cols = dp.shape[-1]
+    rows = dp.numel() // cols
+    ds = torch.empty_like(dp)
+    _count(1)
+    _lib.check(_lib.load().t2h_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), rows, cols, scale, p.shape[0], _stream()))
+    return ds
+
+
+def ce_heads(logits, target, head, w):
+    """logits fp32 [M, nh, ncls]; target/head int64 [M]; w fp32 [M] -> (ce_rows [M] unweighted... see kernel,
+    dlogits fp32 [M, nh*ncls] already multiplied by w)"""
+    _need_cuda(logits)
+    M, nh, ncls = logits.shape
+    loss_rows = torch.empty((M,), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty((M, nh * ncls), dtype=torch.float32, device=logits.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_ce_heads(_ptr(logits), _ptr(target), _ptr(head), _ptr(w), _ptr(loss_rows),
+                                        _ptr(dlogits), M, nh, ncls, _stream()))
+    return loss_rows, dlogits
+
+
+def embed_bwd_(dE, dx, idx=None, t_mod=0):
+    _need_cuda(dE, dx)
+    rows, Cc = dx.shape
+    _count(1)
+    _lib.check(_lib.load().t2h_embed_bwd(_ptr(dx), _ptr(idx), _ptr(dE), rows, Cc, t_mod, _stream()))
+
+
+def adam_(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    _need_cuda(p, g, m, v)
+    _count(1)
+    _lib.check(_lib.load().t2h_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step,
+                                    grad_scale, _stream()))

@@ -1,0 +1,306 @@
+"""Training step of the index-prediction transformer on the B200 kernels, with data-parallel
+gradient all-reduce over NCCL.
+
+Mirrors ``TransformerTextureAwareModel._train_loss`` / ``q_sample`` / ``optimize_parameters``
+(models/transformer_model.py:212-303: absorbing-diffusion masking, 18 masked cross-entropies,
+re-weighted ELBO, ``loss.backward()``, ``torch.optim.Adam.step()``) for the ``TransformerMultiHead``
+mirror.  Forward and backward contractions (dgrad, wgrad, attention gradients) all run on
+``t2h_tapgemm``; operands that a gradient GEMM contracts over rows are transposed by
+``t2h_planes_transpose`` / ``t2h_f32_to_planes_t``.  Parameters, gradients and Adam moments live in flat
+fp32 buffers (the ``nn.Parameter``s are views), so the optimiser is one kernel launch and the gradient
+all-reduce works on contiguous buckets that are launched as soon as the backward pass has finished the
+layers they cover (overlap with the remaining backward).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def targets_from_gt_list(gt_list):
+    """the reference's 18 per-texture ground-truth lists (-1 outside the texture; transformer_model.py:
+    get_quantized_img) -> (own-codebook target [B,T], with -1 where no list covers the position)"""
+    own = torch.full_like(gt_list[0], -1)
+    for gt in gt_list:
+        own = torch.where(gt >= 0, gt, own)
+    return own
+
+
+class SamplerTrainer:
+    """Owns a TransformerMultiHead, its flat parameter / gradient / Adam buffers and the training step."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, num_timesteps=1000, mask_id=None,
+                 loss_type="reweighted_elbo", bucket_layers=6):
+        self.m = model
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.num_timesteps = num_timesteps
+        self.mask_id = model.codebook_size if mask_id is None else mask_id
+        self.loss_type = loss_type
+        self.step_count = 0
+        self.bucket_layers = bucket_layers
+        self.device = next(model.parameters()).device
+        assert model.n_embd % 8 == 0, "flat parameter slots are 32-byte aligned; n_embd must be a multiple of 8"
+        self._handles = []
+        self._flatten()
+
+    # ------------------------------------------------------------------ flat storage
+    def _flatten(self):
+        m = self.m
+        order = [("emb", [m.tok_emb.weight, m.pos_emb, m.segm_emb.weight, m.texture_emb.weight, m.start_tok])]
+        for i, blk in enumerate(m.blocks):
+            a = blk.attn
+            order.append((f"block{i}", [blk.ln1.weight, blk.ln1.bias, a.query.weight, a.key.weight, a.query.bias,
+                                        a.key.bias, a.value.weight, a.value.bias, a.proj.weight, a.proj.bias,
+                                        blk.ln2.weight, blk.ln2.bias, blk.mlp[0].weight, blk.mlp[0].bias,
+                                        blk.mlp[2].weight, blk.mlp[2].bias]))
+        order.append(("head", [m.ln_f.weight, m.ln_f.bias] + [h.weight for h in m.head_list]))
+        total, spans, self.group_span = 0, [], {}
+        for name, ps in order:
+            g0 = total
+            for p in ps:
+                n = (p.numel() + 7) // 8 * 8  # 32-byte aligned slots
+                spans.append((p, total, p.numel()))
+                total += n
+            self.group_span[name] = (g0, total)
+        dev = self.device
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.gview = {}
+        with torch.no_grad():
+            for p, off, n in spans:
+                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)
+                gv = self.flat_g[off:off + n].view_as(p)
+                p.grad = gv
+                self.gview[id(p)] = gv
+        self.n_layers = len(m.blocks)
+
+    def g(self, p):
+        return self.gview[id(p)]
+
+    def _flat_view(self, flat, p, rows, cols):
+        """[rows, cols] view of ``flat`` starting at parameter p's slot (spans adjacent parameters)"""
+        off = self.gview[id(p)].storage_offset()
+        return flat[off:off + rows * cols].view(rows, cols)
+
+    def _weight_planes(self):
+        """fp16 planes of every GEMM weight for this step, as (W [T,1,N,K], W^T [T,1,K,N]) pairs made by
+        one conversion launch each (forward uses W, the data-gradient GEMMs use W^T)"""
+        m = self.m
+        C, F4 = m.n_embd, 4 * m.n_embd
+
+        def pair(p, rows, cols):
+            n, t = ops.f32_to_planes_t(self._flat_view(self.flat_p, p, rows, cols))
+            return n.unsqueeze(1), t.unsqueeze(1)
+
+        wp = []
+        for blk in m.blocks:
+            a = blk.attn
+            wp.append(dict(qk=pair(a.query.weight, 2 * C, C), v=pair(a.value.weight, C, C),
+                           proj=pair(a.proj.weight, C, C), fc1=pair(blk.mlp[0].weight, F4, C),
+                           fc2=pair(blk.mlp[2].weight, C, F4)))
+        heads = pair(m.head_list[0].weight, m.num_head * m.head_class_num, C)
+        return wp, heads
+
+    def _drop_packed_caches(self):
+        # the inference mirrors cache packed weights keyed on torch's version counters, which the raw-pointer
+        # Adam kernel does not bump
+        for mod in self.m.modules():
+            mod.__dict__.pop("_t2h_cache", None)
+
+    # ------------------------------------------------------------------ diffusion bookkeeping (torch RNG)
+    def q_sample(self, x_0, t, generator=None):
+        """mask each token with probability t/T (transformer_model.py:212-230)"""
+        r = torch.rand(x_0.shape, device=x_0.device, generator=generator)
+        mask = r < (t.float().unsqueeze(-1) / self.num_timesteps)
+        x_t = torch.where(mask, torch.full_like(x_0, self.mask_id), x_0)
+        return x_t, mask
+
+    # ------------------------------------------------------------------ forward with saved activations
+    def _forward(self, idx, segm, tex, wp, w_heads):
+        m = self.m
+        B, T = idx.shape
+        C = m.n_embd
+        nh = m.blocks[0].attn.n_head
+        Tt = ops.get_terms()
+        x = ops.embed_sum(idx, segm, tex, m.tok_emb.weight.detach(), m.pos_emb.detach()[0],
+                          m.segm_emb.weight.detach(), m.texture_emb.weight.detach())
+        saved = []
+        for blk in m.blocks:
+            a = blk.attn
+            s = {"x_in": x}
+            h1 = ops.layer_norm(x, blk.ln1.weight.detach(), blk.ln1.bias.detach(), blk.ln1.eps)
+            w = wp[len(saved)]
+            bqk = self._flat_view(self.flat_p, a.query.bias, 1, 2 * C)[0]
+            qk = ops.linear(h1, w["qk"][0], bqk, planes_out=True)
+            vt = ops.bmm_nt(w["v"][0], h1.view(Tt, B, T, C), planes_out=True,
+                            bias_row=a.value.bias.detach(), a_bcast=True)
+            sc = ops.mha_scores(qk, B, T, nh)
+            p = ops.softmax_rows(sc, scale=1.0 / math.sqrt(C // nh))
+            y = ops.mha_pv(p, vt, B, T, nh)
+            x_mid = ops.linear(y, w["proj"][0], a.proj.bias.detach(), residual=x)
+            h2 = ops.layer_norm(x_mid, blk.ln2.weight.detach(), blk.ln2.bias.detach(), blk.ln2.eps)
+            pre = ops.linear(h2, w["fc1"][0], blk.mlp[0].bias.detach())
+            g = ops.gelu_fwd(pre)
+            x = ops.linear(g, w["fc2"][0], blk.mlp[2].bias.detach(), residual=x_mid)
+            s.update(h1=h1, qk=qk, vt=vt, p=p, y=y, x_mid=x_mid, h2=h2, pre=pre, g=g)
+            saved.append(s)
+        hf = ops.layer_norm(x, m.ln_f.weight.detach(), m.ln_f.bias.detach(), m.ln_f.eps)
+        logits = ops.linear(hf, w_heads[0])
+        return logits.view(B * T, m.num_head, m.head_class_num), saved, x, hf
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_and_grads(self, x_0, target_own, segm, tex, t, generator=None, reduce=True, mask=None):
+        """x_0 [B,T] continual tokens; target_own [B,T] each position's index inside its own texture
+        codebook; segm, tex [B,T]; t [B] diffusion times.  Fills the flat gradient buffer (all-reduced over
+        the data-parallel group when ``reduce``) and returns (loss, vb_loss) like the reference."""
+        m = self.m
+        B, T = x_0.shape
+        C = m.n_embd
+        M = B * T
+        nh = m.blocks[0].attn.n_head
+        hs = C // nh
+        Tt = ops.get_terms()
+        scale = 1.0 / math.sqrt(hs)
+        self.flat_g.zero_()
+        self._handles = []
+
+        if mask is None:
+            x_t, mask = self.q_sample(x_0, t, generator)
+        else:
+            x_t = torch.where(mask, torch.full_like(x_0, self.mask_id), x_0)
+        wp, w_heads = self._weight_planes()
+        logits, saved, x_last, hf = self._forward(x_t, segm, tex, wp, w_heads)
+
+        # ---- re-weighted ELBO over the masked positions' own heads (transformer_model.py:250-270)
+        tgt = torch.where(mask, target_own, torch.full_like(target_own, -1)).reshape(-1).contiguous()
+        tf = t.float()
+        if self.loss_type == "reweighted_elbo":
+            wb = (1.0 - tf / self.num_timesteps) / (math.log(2) * T)
+        elif self.loss_type == "elbo":
+            wb = self.num_timesteps / tf / (math.log(2) * T)
+        else:
+            raise NotImplementedError(self.loss_type)
+        w_rows = (wb / B).repeat_interleave(T).contiguous()
+        ce_rows, dlogits = ops.ce_heads(logits, tgt, tex.reshape(-1).contiguous(), w_rows)
+        ce_b = ce_rows.view(B, T).sum(1)
+        loss = (wb * ce_b).mean()
+        vb_loss = (ce_b * self.num_timesteps / tf / (math.log(2) * T)).mean()
+
+        # ---- heads + final LayerNorm
+        NK = m.num_head * m.head_class_num
+        dl_n, dl_t = ops.f32_to_planes_t(dlogits)                       # [Tt,M,NK], [Tt,NK,M]
+        hf_t = ops.planes_transpose(hf.unsqueeze(1))[:, 0]              # [Tt,C,M]
+        g_heads = self._flat_view(self.flat_g, m.head_list[0].weight, NK, C)
+        ops.linear(dl_t, hf_t.unsqueeze(1), out=g_heads)                # dW_heads = dlogits^T hf
+        d_hf = ops.linear(dl_n, w_heads[1])                             # [M, C]
+        del dlogits, dl_n, dl_t
+        dx = torch.zeros((M, C), dtype=torch.float32, device=x_0.device)  # running gradient of the stream
+        ops.layernorm_bwd_(dx, d_hf, x_last, m.ln_f.weight.detach(), self.g(m.ln_f.weight), self.g(m.ln_f.bias),
+                           m.ln_f.eps, accumulate=False)
+        self._bucket_done("head", reduce)
+
+        # ---- blocks, last to first; dx is updated in place
+        for li in range(self.n_layers - 1, -1, -1):
+            blk, s, w = m.blocks[li], saved[li], wp[li]
+            a = blk.attn
+            fc1, fc2 = blk.mlp[0], blk.mlp[2]
+            # MLP: x_out = x_mid + fc2(gelu(fc1(ln2(x_mid))))
+            dxo_n, dxo_t = ops.f32_to_planes_t(dx)
+            ops.colsum_(self.g(fc2.bias), dx)
+            g_t = ops.planes_transpose(s["g"].unsqueeze(1))[:, 0]                       # [Tt,F,M]
+            ops.linear(dxo_t, g_t.unsqueeze(1), out=self.g(fc2.weight))                   # dW2 [C,F]
+            d_g = ops.linear(dxo_n, w["fc2"][1])                                            # [M,F]
+            d_a = ops.gelu_bwd(s["pre"], d_g)
+            da_n, da_t = ops.f32_to_planes_t(d_a)
+            ops.colsum_(self.g(fc1.bias), d_a)
+            h2_t = ops.planes_transpose(s["h2"].unsqueeze(1))[:, 0]                      # [Tt,C,M]
+            ops.linear(da_t, h2_t.unsqueeze(1), out=self.g(fc1.weight))                   # dW1 [F,C]
+            d_h2 = ops.linear(da_n, w["fc1"][1])                                            # [M,C]
+            ops.layernorm_bwd_(dx, d_h2, s["x_mid"], blk.ln2.weight.detach(), self.g(blk.ln2.weight),
+                               self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True)       # dx = d x_mid
+            # attention output projection: x_mid = x_in + proj(y)
+            dxm_n, dxm_t = ops.f32_to_planes_t(dx)
+            ops.colsum_(self.g(a.proj.bias), dx)
+            y_t = ops.planes_transpose(s["y"].unsqueeze(1))[:, 0]
+            ops.linear(dxm_t, y_t.unsqueeze(1), out=self.g(a.proj.weight))                # dWp [C,C]
+            dyv = torch.empty((Tt, M, 2 * C), dtype=torch.float16, device=dx.device)      # [d_y | v]
+            ops.linear(dxm_n, w["proj"][1], planes_out=True, out=dyv[:, :, :C])            # d_y
+            ops.planes_transpose(s["vt"], out=dyv.view(Tt, B, T, 2 * C)[..., C:])         # v token-major
+            # attention core
+            dy_t = ops.planes_transpose(dyv.view(Tt, B, T, 2 * C)[..., :C])               # [Tt,B,C,T]
+            p_t = ops.planes_transpose(s["p"].view(Tt, B * nh, T, T)).view(Tt, B, nh, T, T)
+            dv = ops.mha_pv(p_t, dy_t, B, T, nh, planes_out=False)                        # fp32 [M,C]
+            dp = ops.mha_scores(dyv, B, T, nh)                                            # [B,nh,T,T]
+            ds = ops.softmax_bwd(s["p"], dp, scale)
+            ds_n, ds_t = ops.f32_to_planes_t(ds.view(B * nh, T, T))
+            qk4 = s["qk"].view(Tt, B, T, 2 * C)
+            k_t = ops.planes_transpose(qk4[..., C:])                                      # [Tt,B,C,T]
+            q_t = ops.planes_transpose(qk4[..., :C])
+            d_qk = torch.empty((M, 2 * C), dtype=torch.float32, device=dx.device)
+            ops.mha_pv(ds_n.view(Tt, B, nh, T, T), k_t, B, T, nh, planes_out=False, out=d_qk[:, :C])   # dQ
+            ops.mha_pv(ds_t.view(Tt, B, nh, T, T), q_t, B, T, nh, planes_out=False, out=d_qk[:, C:])   # dK
+            # q|k projection
+            dqk_n, dqk_t = ops.f32_to_planes_t(d_qk)
+            ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 2 * C)[0], d_qk)     # [q.bias | k.bias]
+            h1_t = ops.planes_transpose(s["h1"].unsqueeze(1))[:, 0]                       # [Tt,C,M]
+            ops.linear(dqk_t, h1_t.unsqueeze(1), out=self._flat_view(self.flat_g, a.query.weight, 2 * C, C))
+            d_h1 = ops.linear(dqk_n, w["qk"][1])                                          # [M,C]
+            # v projection
+            dv_n, dv_t = ops.f32_to_planes_t(dv)
+            ops.colsum_(self.g(a.value.bias), dv)
+            ops.linear(dv_t, h1_t.unsqueeze(1), out=self.g(a.value.weight))               # dWv [C,C]
+            d_h1 = ops.linear(dv_n, w["v"][1], residual=d_h1)
+            ops.layernorm_bwd_(dx, d_h1, s["x_in"], blk.ln1.weight.detach(), self.g(blk.ln1.weight),
+                               self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True)       # dx = d x_in
+            saved[li] = None
+            if li % self.bucket_layers == 0:
+                hi = min(self.n_layers, li + self.bucket_layers)
+                self._bucket_done((li, hi), reduce)
+
+        # ---- embeddings
+        ops.embed_bwd_(self.g(m.tok_emb.weight), dx, x_t.reshape(-1).contiguous())
+        ops.embed_bwd_(self.g(m.pos_emb).view(-1, C), dx, None, T)
+        ops.embed_bwd_(self.g(m.segm_emb.weight), dx, segm.reshape(-1).contiguous())
+        ops.embed_bwd_(self.g(m.texture_emb.weight), dx, tex.reshape(-1).contiguous())
+        self._bucket_done("emb", reduce)
+        self.wait_reduced()
+        return loss, vb_loss
+
+    def wait_reduced(self):
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    def _bucket_done(self, which, reduce):
+        """gradients of a contiguous slice of the flat buffer are final: start their all-reduce (sum) now,
+        asynchronously, so it overlaps the rest of the backward pass"""
+        if not (reduce and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if isinstance(which, tuple):
+            a = self.group_span[f"block{which[0]}"][0]
+            b = self.group_span[f"block{which[1] - 1}"][1]
+        else:
+            a, b = self.group_span[which]
+        self._handles.append(dist.all_reduce(self.flat_g[a:b], op=dist.ReduceOp.SUM, async_op=True))
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self):
+        """torch.optim.Adam(lr, weight_decay=0) on the flat buffers; gradients averaged over ranks"""
+        self.step_count += 1
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        ops.adam_(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1],
+                  self.eps, self.step_count, grad_scale=1.0 / world)
+        self._drop_packed_caches()
+
+    def optimize_parameters(self, x_0, target_own, segm, tex, generator=None):
+        """one reference training step: sample t ~ U{1..T}, loss, backward, all-reduce, Adam"""
+        B = x_0.shape[0]
+        t = torch.randint(1, self.num_timesteps + 1, (B,), device=x_0.device, generator=generator)
+        loss, vb = self.loss_and_grads(x_0, target_own, segm, tex, t, generator)
+        self.adam_step()
+        return loss, vb
