@@ -243,9 +243,10 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
  *  loss.backward() + torch.optim.Adam.step()).  Dense gradients (dgrad / wgrad / attention) run on
  * t2h_tapgemm; these are the HBM-bound pieces around it.
  * ---------------------------------------------------------------------- */
-/* fp32 [g][r][c] -> fp16 planes transposed out_t[terms][g][c][r] (+ untransposed out_n, may be NULL):
- * wgrad contracts over rows, so both operands are needed row-contiguous */
-int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms,
+/* fp32 [g][r][c] -> fp16 planes of scale*x, transposed out_t[terms][g][c][r] (+ untransposed out_n, may be
+ * NULL): wgrad contracts over rows, so both operands are needed row-contiguous.  `scale` (a power of two,
+ * undone by the consuming GEMM's alpha) keeps small gradients out of fp16's subnormal range */
+int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms, float scale,
                         t2h_stream_t stream);
 /* fp16 planes [terms][g][r][c] (row stride ld, group stride g_stride, plane stride in_plane, elements)
  * -> [terms][g][c][r] with output row stride out_ld, group stride out_g_stride, plane stride out_plane */

@@ -36,6 +36,8 @@ def _rel(got, want):
 def test_f32_to_planes_t_and_planes_transpose(shape):
     ops = _ops()
     x = torch.randn(shape, device=DEV)
+    n4, t4 = ops.f32_to_planes_t(1e-6 * x, scale=2.0 ** 20)     # scaled conversion of small gradients
+    assert _rel(_join(n4), 1e-6 * x * 2.0 ** 20) < 1e-6 and torch.equal(t4, n4.transpose(2, 3).contiguous())
     n, t = ops.f32_to_planes_t(x)
     assert _rel(_join(n), x) < 1e-6 and _rel(_join(t), x.transpose(1, 2)) < 1e-6
     assert torch.equal(t, n.transpose(2, 3).contiguous())          # same split, only moved
@@ -141,13 +143,16 @@ def _make(cfg, seed):
     return net, sd, SamplerTrainer(net)
 
 
-def _grad_report(net, want_grads):
+def _grad_report(net, want_grads, loss_scale):
+    """max error of every gradient tensor relative to its own max; tensors whose true gradient vanishes
+    (key.bias: softmax is invariant to it; start_tok: unused) are measured against the typical scale"""
     rows, worst = [], 0.0
+    typical = float(np.median([float(w.abs().max()) for w in want_grads.values()]))
     for k, p in net.named_parameters():
         want = want_grads[k].to(DEV)
-        e = float((p.grad - want).abs().max())
-        scale = float(want.abs().max())
-        rel = e / scale if scale > 0 else e
+        e = float((p.grad / loss_scale - want).abs().max())
+        scale = max(float(want.abs().max()), 0.05 * typical)
+        rel = e / scale
         rows.append(f"{k:40s} |g|max {scale:.3e} err {e:.3e} rel {rel:.2e}")
         worst = max(worst, rel)
     return worst, "\n".join(rows)
@@ -166,15 +171,19 @@ def test_train_step_matches_reference_fixture():
     loss, vb = tr.loss_and_grads(x_0, targets_from_gt_list(gt_list), segm, tex, t, mask=mask)
     assert abs(float(loss) - float(gold["loss"])) <= 1e-4 * abs(float(gold["loss"]))
     assert abs(float(vb) - float(gold["vb_loss"])) <= 1e-4 * abs(float(gold["vb_loss"]))
-    worst, rep = _grad_report(net, {k: torch.from_numpy(gold["grad/" + k]) for k, _ in net.named_parameters()})
+    worst, rep = _grad_report(net, {k: torch.from_numpy(gold["grad/" + k]) for k, _ in net.named_parameters()},
+                              tr.loss_scale)
     assert worst <= 1e-3, "\n" + rep
     # one Adam step: compare the parameter moves with the real torch.optim.Adam's
     tr.adam_step()
+    typical = float(np.median([float(np.abs(gold["grad/" + k]).max()) for k, _ in net.named_parameters()]))
     for k, p in net.named_parameters():
         d_want = torch.from_numpy(gold["param1/" + k]) - sd[k]
         d_got = p.detach().cpu() - sd[k]
         g = torch.from_numpy(gold["grad/" + k]).abs()
-        sel = g > 1e-3 * g.max()          # Adam's sign-like first step amplifies noise on ~zero gradients
+        # Adam's sign-like first step turns rounding noise on (mathematically) zero gradients into +-lr
+        # moves in the reference too (key.bias, start_tok): compare only where a gradient exists
+        sel = (g > 1e-3 * g.max()) & (g > 1e-4 * typical)
         if sel.any():
             assert float((d_got - d_want)[sel].abs().max()) <= 0.02 * 1e-4, k
     # the inference mirror sees the updated weights (packed-plane caches were dropped)
@@ -205,7 +214,7 @@ def test_train_step_matches_autograd_of_restatement_mid_shape():
                                  t.to(DEV), mask=mask.to(DEV))
     assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
     assert abs(float(vb) - float(vb_ref)) <= 1e-4 * abs(float(vb_ref))
-    worst, rep = _grad_report(net, want)
+    worst, rep = _grad_report(net, want, tr.loss_scale)
     assert worst <= 1e-3, "\n" + rep
 
 

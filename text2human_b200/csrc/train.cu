@@ -12,14 +12,15 @@ namespace t2h {
 
 // fp32 [G][R][C] -> fp16 planes, transposed: out[t][g][c][r]   (and optionally the untransposed planes)
 __global__ void f32_to_planes_t_kernel(const float* __restrict__ x, __half* __restrict__ out_t,
-                                       __half* __restrict__ out_n, int R, int C, int terms, long long plane) {
+                                       __half* __restrict__ out_n, int R, int C, int terms, long long plane,
+                                       float scale) {
   __shared__ float tile[32][33];
   const int g = blockIdx.z;
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* xg = x + (long long)g * R * C;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    const float v = (r < R && c < C) ? xg[(long long)r * C + c] : 0.f;
+    const float v = (r < R && c < C) ? scale * xg[(long long)r * C + c] : 0.f;
     tile[i][threadIdx.x] = v;
     if (out_n && r < R && c < C) {
       __half hi, lo;
@@ -297,13 +298,14 @@ using namespace t2h;
 
 extern "C" {
 
-int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms,
+int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms, float scale,
                         t2h_stream_t stream) {
   T2H_CHECK_ARG(x && out_t && g > 0 && r > 0 && c > 0, "f32_to_planes_t: bad args");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "f32_to_planes_t: terms=%d", terms);
   dim3 grid(ceil_div(r, 32), ceil_div(c, 32), g), block(32, 8);
   f32_to_planes_t_kernel<<<grid, block, 0, as_stream(stream)>>>(
-      x, reinterpret_cast<__half*>(out_t), reinterpret_cast<__half*>(out_n), r, c, terms, (long long)g * r * c);
+      x, reinterpret_cast<__half*>(out_t), reinterpret_cast<__half*>(out_n), r, c, terms, (long long)g * r * c,
+      scale);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

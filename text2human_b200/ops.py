@@ -328,7 +328,7 @@ def mha_scores(qk, B, Tn, nh, alpha=1.0):
     return out
 
 
-def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True):
+def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True, alpha=1.0):
     """Multi-head att @ v (transformer_arch.py:65-67).  p: planes [T,B,nh,Tn,Tn];
     vt: planes [T,B,C,Tn] (v transposed: channels x tokens).  -> planes [T, B*Tn, C] (or fp32 [B*Tn, C])
     with the heads re-assembled side by side.  ``out`` may be a column-sliced view of a wider matrix."""
@@ -346,7 +346,7 @@ def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True):
              b=vt, b_term_g=B, b_groups=T * B, b_sg=Cc * Tn, b_batched_h=1,
              b_groups2=nh, b_sg2=hs * Tn, b_batched=1, n_out=hs, b_sn=Tn,
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=(hs, Tn * ld, ld, 1),
-             d_plane=out.stride(0) if planes_out else 0)
+             d_plane=out.stride(0) if planes_out else 0, alpha=alpha)
     return out
 
 
@@ -564,8 +564,8 @@ def vq_gather(codebook, idx, book_id, *, B, Hz, Wz, Cz, ps=1, want_nchw=True, wa
 # ----------------------------------------------------------------------------
 # training (backward / optimiser) kernels
 # ----------------------------------------------------------------------------
-def f32_to_planes_t(x, terms=None, want_plain=True):
-    """fp32 [G,R,C] (or [R,C]) -> (planes [T,G,R,C] or None, transposed planes [T,G,C,R])"""
+def f32_to_planes_t(x, terms=None, want_plain=True, scale=1.0):
+    """fp32 [G,R,C] (or [R,C]) -> (planes [T,G,R,C] or None, transposed planes [T,G,C,R]) of scale*x"""
     _need_cuda(x)
     terms = terms or get_terms()
     x3 = x if x.dim() == 3 else x.unsqueeze(0)
@@ -574,7 +574,8 @@ def f32_to_planes_t(x, terms=None, want_plain=True):
     out_t = torch.empty((terms, G, Cc, R), dtype=torch.float16, device=x.device)
     out_n = torch.empty((terms, G, R, Cc), dtype=torch.float16, device=x.device) if want_plain else None
     _count(1)
-    _lib.check(_lib.load().t2h_f32_to_planes_t(_ptr(x3), _ptr(out_t), _ptr(out_n), G, R, Cc, terms, _stream()))
+    _lib.check(_lib.load().t2h_f32_to_planes_t(_ptr(x3), _ptr(out_t), _ptr(out_n), G, R, Cc, terms, scale,
+                                                 _stream()))
     if x.dim() == 2:
         return (out_n[:, 0] if want_plain else None), out_t[:, 0]
     return out_n, out_t

@@ -39,6 +39,7 @@ class SamplerTrainer:
         self.mask_id = model.codebook_size if mask_id is None else mask_id
         self.loss_type = loss_type
         self.step_count = 0
+        self.loss_scale = 1.0
         self.bucket_layers = bucket_layers
         self.device = next(model.parameters()).device
         assert model.n_embd % 8 == 0, "flat parameter slots are 32-byte aligned; n_embd must be a multiple of 8"
@@ -157,7 +158,8 @@ class SamplerTrainer:
     def loss_and_grads(self, x_0, target_own, segm, tex, t, generator=None, reduce=True, mask=None):
         """x_0 [B,T] continual tokens; target_own [B,T] each position's index inside its own texture
         codebook; segm, tex [B,T]; t [B] diffusion times.  Fills the flat gradient buffer (all-reduced over
-        the data-parallel group when ``reduce``) and returns (loss, vb_loss) like the reference."""
+        the data-parallel group when ``reduce``) and returns (loss, vb_loss) like the reference.  The
+        gradients (``p.grad`` views) are left multiplied by ``self.loss_scale``; ``adam_step`` divides."""
         m = self.m
         B, T = x_0.shape
         C = m.n_embd
@@ -168,6 +170,13 @@ class SamplerTrainer:
         scale = 1.0 / math.sqrt(hs)
         self.flat_g.zero_()
         self._handles = []
+        # Static loss scale (a power of two, undone inside the Adam kernel): the gradient operands of the
+        # backward GEMMs are fp16 hi/lo planes, whose absolute resolution is 2^-24; scaling the loss so that
+        # |dlogits| <= 256 keeps every gradient tensor well inside fp16's normal range.  The bound on the
+        # per-row loss weight is known on the host, so no device->host sync is needed to choose it.
+        w_bound = (1.0 if self.loss_type == "reweighted_elbo" else float(self.num_timesteps)) / (math.log(2) * T * B)
+        S = self.loss_scale = 2.0 ** math.floor(math.log2(256.0 / w_bound))
+        DS = 256.0  # extra scale of the (much smaller) score gradients, undone by the consuming GEMMs' alpha
 
         if mask is None:
             x_t, mask = self.q_sample(x_0, t, generator)
@@ -185,7 +194,7 @@ class SamplerTrainer:
             wb = self.num_timesteps / tf / (math.log(2) * T)
         else:
             raise NotImplementedError(self.loss_type)
-        w_rows = (wb / B).repeat_interleave(T).contiguous()
+        w_rows = (wb * (S / B)).repeat_interleave(T).contiguous()
         ce_rows, dlogits = ops.ce_heads(logits, tgt, tex.reshape(-1).contiguous(), w_rows)
         ce_b = ce_rows.view(B, T).sum(1)
         loss = (wb * ce_b).mean()
@@ -237,13 +246,15 @@ class SamplerTrainer:
             dv = ops.mha_pv(p_t, dy_t, B, T, nh, planes_out=False)                        # fp32 [M,C]
             dp = ops.mha_scores(dyv, B, T, nh)                                            # [B,nh,T,T]
             ds = ops.softmax_bwd(s["p"], dp, scale)
-            ds_n, ds_t = ops.f32_to_planes_t(ds.view(B * nh, T, T))
+            ds_n, ds_t = ops.f32_to_planes_t(ds.view(B * nh, T, T), scale=DS)
             qk4 = s["qk"].view(Tt, B, T, 2 * C)
             k_t = ops.planes_transpose(qk4[..., C:])                                      # [Tt,B,C,T]
             q_t = ops.planes_transpose(qk4[..., :C])
             d_qk = torch.empty((M, 2 * C), dtype=torch.float32, device=dx.device)
-            ops.mha_pv(ds_n.view(Tt, B, nh, T, T), k_t, B, T, nh, planes_out=False, out=d_qk[:, :C])   # dQ
-            ops.mha_pv(ds_t.view(Tt, B, nh, T, T), q_t, B, T, nh, planes_out=False, out=d_qk[:, C:])   # dK
+            ops.mha_pv(ds_n.view(Tt, B, nh, T, T), k_t, B, T, nh, planes_out=False, out=d_qk[:, :C],
+                       alpha=1.0 / DS)                                                    # dQ
+            ops.mha_pv(ds_t.view(Tt, B, nh, T, T), q_t, B, T, nh, planes_out=False, out=d_qk[:, C:],
+                       alpha=1.0 / DS)                                                    # dK
             # q|k projection
             dqk_n, dqk_t = ops.f32_to_planes_t(d_qk)
             ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 2 * C)[0], d_qk)     # [q.bias | k.bias]
@@ -294,7 +305,7 @@ class SamplerTrainer:
         self.step_count += 1
         world = dist.get_world_size() if dist.is_initialized() else 1
         ops.adam_(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1],
-                  self.eps, self.step_count, grad_scale=1.0 / world)
+                  self.eps, self.step_count, grad_scale=1.0 / (world * self.loss_scale))
         self._drop_packed_caches()
 
     def optimize_parameters(self, x_0, target_own, segm, tex, generator=None):
