@@ -126,6 +126,10 @@ typedef struct t2h_tapgemm_params {
   double* gn_stats;      /* optional [n_img][32][2] (sum, sumsq) accumulators
                             of the fp32 output, for the following GroupNorm   */
   int32_t gn_cpg;        /* channels per group when gn_stats != NULL         */
+  int32_t k_split;       /* >= 2: split the contraction of every output tile over up to k_split CTAs whose
+                            partial sums are reduce-added (TMA .add) into D, which the caller has zeroed
+                            (weight gradients: few output tiles, contraction over all tokens).  Needs a
+                            16-byte-aligned fp32 D and no bias/act/residual/gn_stats.  0/1: off        */
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);

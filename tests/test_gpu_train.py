@@ -32,7 +32,7 @@ def _rel(got, want):
 
 
 # ----------------------------------------------------------------------------- kernels
-@pytest.mark.parametrize("shape", [(1, 64, 64), (3, 50, 72), (2, 512, 40)])
+@pytest.mark.parametrize("shape", [(1, 64, 64), (3, 50, 72), (2, 512, 40), (2, 33, 47), (1, 130, 65)])
 def test_f32_to_planes_t_and_planes_transpose(shape):
     ops = _ops()
     x = torch.randn(shape, device=DEV)
@@ -51,6 +51,29 @@ def test_f32_to_planes_t_and_planes_transpose(shape):
         ops.planes_transpose(n[..., half:], out=wide[..., Rr:])
         assert torch.equal(wide[..., Rr:], n[..., half:].transpose(2, 3))
         assert float(wide[..., :Rr].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 256), (512, 512, 8192), (1024, 512, 4104), (96, 200, 1000)])
+def test_split_k_weight_gradient_gemm(M, N, K):
+    """k-slices reduce-added by TMA into a zeroed output == the unsplit contraction"""
+    ops = _ops()
+    dy = torch.randn(K, M, device=DEV)
+    x = torch.randn(K, N, device=DEV)
+    _, dy_t = ops.f32_to_planes_t(dy, want_plain=False)
+    _, x_t = ops.f32_to_planes_t(x, want_plain=False)
+    ks = ops.wgrad_k_split(M, N, K)
+    assert ks >= 2
+    out = torch.zeros(M, N, device=DEV)
+    ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)
+    plain = ops.linear(dy_t, x_t.unsqueeze(1))
+    want = dy.double().t() @ x.double()
+    assert _rel(plain, want) < 1e-4                                # the 3-product split's own accuracy
+    assert _rel(out, want) < 1e-4
+    assert _rel(out, plain) < 2e-6                                 # only the summation order differs
+    ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)       # accumulates: twice the gradient
+    assert _rel(out, 2 * plain) < 2e-6
+    with pytest.raises(Exception):
+        ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks, bias=torch.zeros(N, device=DEV))
 
 
 def test_colsum_gelu_layernorm_softmax_backward_kernels():

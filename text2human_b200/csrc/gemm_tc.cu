@@ -33,6 +33,7 @@ struct TapGemmDev {
   int TW, TH;  // spatial box of one 128-row block
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int n_out, C, kchunks, nterms;
+  int ksplit, kper, total_work;  // split-K: work item = (tile, k-slice); total_work = total_tiles * ksplit
   int a_term_imgs, a_bcast, b_term_g, b_batched, b_batched_h;
   // taps grouped by (dx, img_off): one activation slab per group
   int ngroups, slab_rows;
@@ -207,11 +208,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------- A producer (activation slabs)
     if (lane == 0) {
       int sa = 0, pa = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+        const int tile = work % P.total_tiles;
+        const int ch0 = (work / P.total_tiles) * P.kper;
+        const int ch1 = min(P.kchunks, ch0 + P.kper);
         const TileCoord t = decode_tile(P, tile, MBLK, BN);
         const int a_img = P.a_bcast ? 0 : t.img;
         for (int g = 0; g < P.ngroups; ++g) {
-          for (int ch = 0; ch < P.kchunks; ++ch) {
+          for (int ch = ch0; ch < ch1; ++ch) {
             for (int pl = 0; pl < a_planes; ++pl) {  // hi, then lo
               mbar_wait(&a_empty[sa], pa ^ 1);
               if (P.debug & 4) {
@@ -235,12 +239,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int sb = 0, pb = 0;
       const int b_planes = a_planes;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+        const int tile = work % P.total_tiles;
+        const int ch0 = (work / P.total_tiles) * P.kper;
+        const int ch1 = min(P.kchunks, ch0 + P.kper);
         const TileCoord t = decode_tile(P, tile, MBLK, BN);
         const int b_g2 = P.b_batched ? t.img : 0;
         const int b_g = P.b_batched_h ? t.h0 : 0;
         for (int g = 0; g < P.ngroups; ++g) {
-          for (int ch = 0; ch < P.kchunks; ++ch) {
+          for (int ch = ch0; ch < ch1; ++ch) {
             for (int tp = 0; tp < P.g_ntaps[g]; ++tp) {
               for (int pl = b_planes - 1; pl >= 0; --pl) {  // lo first, then hi (consumption order)
                 mbar_wait(&b_empty[sb], pb ^ 1);
@@ -275,7 +282,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool dbg_nomma = (P.debug & 2) != 0;
       const int ngroups = P.ngroups, kchunks = P.kchunks;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+        const int tile = work % P.total_tiles;
+        const int ch0 = (work / P.total_tiles) * P.kper;
+        const int ch1 = min(P.kchunks, ch0 + P.kper);
         mbar_wait(&tempty_bar[as], ap ^ 1);
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * C::kAccCols;
@@ -293,7 +303,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nt = P.g_ntaps[g];
           const uint32_t dy0 = P.g_dyrel[g][0] * row16, dy1 = P.g_dyrel[g][1] * row16,
                          dy2 = P.g_dyrel[g][2] * row16;
-          for (int ch = 0; ch < kchunks; ++ch) {
+          for (int ch = ch0; ch < ch1; ++ch) {
             const int ksteps = (ch == kchunks - 1) ? last_steps : 4;
             // slab slots of this (group, chunk)
             const int sa_hi = sa, pa_hi = pa;
@@ -355,7 +365,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t res_par[2] = {0, 0};
     int tile_par = 0;  // gsum buffer of this tile
 
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+        const int tile = work % P.total_tiles;
+        const int ch0 = (work / P.total_tiles) * P.kper;
+        const int ch1 = min(P.kchunks, ch0 + P.kper);
       const TileCoord t = decode_tile(P, tile, MBLK, BN);
 
       if (P.epi_mode == EPI_TMA_F32) {
@@ -449,7 +462,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           named_bar_sync(2, 128);  // staging tile complete; residual tile fully consumed
           if (elected) {
-            tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);
+            if (P.ksplit > 1)
+              tma_reduce_add_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);  // partial sum of a k-slice
+            else
+              tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);
             tma_store_commit();
             if (has_res && u + 2 < nunits) issue_res(u + 2, buf);
             tma_store_wait_read<1>();  // the other staging tile is free again
@@ -702,7 +718,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   if (Q.b_slots < 3) return fail(T2H_EINVAL, "tapgemm: shared-memory rings do not fit");
-  int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  int grid = P.total_work < num_sms() ? P.total_work : num_sms();
   // the full dynamic allocation also keeps it to one CTA (one TMEM allocation) per SM
   tapgemm_kernel<BN, MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
   T2H_LAUNCH_OK();
@@ -883,6 +899,19 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   if (p->bias_mode == T2H_BIAS_COL) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0);
   P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
   if (swap) P.epi_mode = swap_direct ? EPI_DIRECT : EPI_TMA_F32;
+  // ---- split-K: k-slices of one tile go to different CTAs and are reduce-added into a zeroed output
+  P.ksplit = 1;
+  P.kper = P.kchunks;
+  if (p->k_split > 1 && !swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode == T2H_BIAS_NONE &&
+      p->act == T2H_ACT_NONE && !p->gn_stats) {
+    int ks = p->k_split < P.kchunks ? p->k_split : P.kchunks;
+    P.kper = ceil_div(P.kchunks, ks);
+    P.ksplit = ceil_div(P.kchunks, P.kper);
+  } else {
+    T2H_CHECK_ARG(p->k_split <= 1, "tapgemm: k_split needs a plain aligned fp32 output (no bias/act/residual)");
+  }
+  T2H_CHECK_ARG((long long)P.total_tiles * P.ksplit < (1LL << 31), "tapgemm: too many work items");
+  P.total_work = P.total_tiles * P.ksplit;
   if (p->gn_stats && !swap) {
     T2H_CHECK_ARG(P.epi_mode == EPI_TMA_F32, "tapgemm: gn_stats needs an aligned fp32 NHWC output");
     T2H_CHECK_ARG(p->gn_cpg >= 2 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0,

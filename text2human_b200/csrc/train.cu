@@ -10,59 +10,115 @@
 
 namespace t2h {
 
-// fp32 [G][R][C] -> fp16 planes, transposed: out[t][g][c][r]   (and optionally the untransposed planes)
+// fp32 [G][R][C] -> fp16 planes of scale*x, transposed: out_t[t][g][c][r] (and optionally the untransposed
+// planes out_n).  64x64 tiles; 8-byte loads, 4-byte stores when R and C are even (else a scalar tail path).
 __global__ void f32_to_planes_t_kernel(const float* __restrict__ x, __half* __restrict__ out_t,
                                        __half* __restrict__ out_n, int R, int C, int terms, long long plane,
                                        float scale) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[64][65];
   const int g = blockIdx.z;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const float* xg = x + (long long)g * R * C;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    const float v = (r < R && c < C) ? scale * xg[(long long)r * C + c] : 0.f;
-    tile[i][threadIdx.x] = v;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const bool vec_c = (C & 1) == 0, vec_r = (R & 1) == 0;
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (r < R) {
+      if (vec_c && c + 1 < C) {
+        const float2 v = *reinterpret_cast<const float2*>(xg + (long long)r * C + c);
+        v0 = v.x * scale;
+        v1 = v.y * scale;
+      } else {
+        if (c < C) v0 = xg[(long long)r * C + c] * scale;
+        if (c + 1 < C) v1 = xg[(long long)r * C + c + 1] * scale;
+      }
+    }
+    tile[i][2 * tx] = v0;
+    tile[i][2 * tx + 1] = v1;
     if (out_n && r < R && c < C) {
-      __half hi, lo;
-      split_f16(v, hi, lo);
+      __half h0, l0, h1, l1;
+      split_f16(v0, h0, l0);
+      split_f16(v1, h1, l1);
       const long long o = (long long)g * R * C + (long long)r * C + c;
-      out_n[o] = hi;
-      if (terms == 2) out_n[plane + o] = lo;
+      if (vec_c && c + 1 < C) {
+        *reinterpret_cast<__half2*>(out_n + o) = __halves2half2(h0, h1);
+        if (terms == 2) *reinterpret_cast<__half2*>(out_n + plane + o) = __halves2half2(l0, l1);
+      } else {
+        out_n[o] = h0;
+        if (terms == 2) out_n[plane + o] = l0;
+        if (c + 1 < C) {
+          out_n[o + 1] = h1;
+          if (terms == 2) out_n[plane + o + 1] = l1;
+        }
+      }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < R && c < C) {
-      __half hi, lo;
-      split_f16(tile[threadIdx.x][i], hi, lo);
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c < C && r < R) {
+      __half h0, l0, h1, l1;
+      split_f16(tile[2 * tx][i], h0, l0);
+      split_f16(tile[2 * tx + 1][i], h1, l1);
       const long long o = (long long)g * R * C + (long long)c * R + r;
-      out_t[o] = hi;
-      if (terms == 2) out_t[plane + o] = lo;
+      if (vec_r && r + 1 < R) {
+        *reinterpret_cast<__half2*>(out_t + o) = __halves2half2(h0, h1);
+        if (terms == 2) *reinterpret_cast<__half2*>(out_t + plane + o) = __halves2half2(l0, l1);
+      } else {
+        out_t[o] = h0;
+        if (terms == 2) out_t[plane + o] = l0;
+        if (r + 1 < R) {
+          out_t[o + 1] = h1;
+          if (terms == 2) out_t[plane + o + 1] = l1;
+        }
+      }
     }
   }
 }
 
-// fp16 planes [T][G][R][C] (row stride ld, column offset applied by the caller) -> [T][G][C][R]
+// fp16 planes [T][G][R][C] (row stride ld, column offset applied by the caller) -> [T][G][C][R].
+// 64x64 tiles, one plane per blockIdx.z slice; 4-byte accesses when the strides and bases allow it.
 __global__ void planes_transpose_kernel(const __half* __restrict__ x, __half* __restrict__ out, int R, int C,
-                                        long long ld, long long g_stride, long long in_plane, int terms,
-                                        long long out_ld, long long out_g_stride, long long out_plane) {
-  __shared__ __half tile[2][32][34];
-  const int g = blockIdx.z;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int t = 0; t < terms; ++t) {
-    const __half* xg = x + t * in_plane + (long long)g * g_stride;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int r = r0 + i, c = c0 + threadIdx.x;
-      tile[t][i][threadIdx.x] = (r < R && c < C) ? xg[(long long)r * ld + c] : __float2half(0.f);
+                                        long long ld, long long g_stride, long long in_plane, int G,
+                                        long long out_ld, long long out_g_stride, long long out_plane, int vec_in,
+                                        int vec_out) {
+  __shared__ __half tile[64][66];
+  const int t = blockIdx.z / G, g = blockIdx.z - t * G;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const __half* xg = x + t * in_plane + (long long)g * g_stride;
+  __half* og = out + t * out_plane + (long long)g * out_g_stride;
+  const __half zero = __float2half(0.f);
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    __half a = zero, b = zero;
+    if (r < R) {
+      if (vec_in && c + 1 < C) {
+        const __half2 v = *reinterpret_cast<const __half2*>(xg + (long long)r * ld + c);
+        a = __low2half(v);
+        b = __high2half(v);
+      } else {
+        if (c < C) a = xg[(long long)r * ld + c];
+        if (c + 1 < C) b = xg[(long long)r * ld + c + 1];
+      }
     }
+    *reinterpret_cast<__half2*>(&tile[i][2 * tx]) = __halves2half2(a, b);
   }
   __syncthreads();
-  for (int t = 0; t < terms; ++t)
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < R && c < C) out[t * out_plane + (long long)g * out_g_stride + (long long)c * out_ld + r] = tile[t][threadIdx.x][i];
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c < C && r < R) {
+      const __half a = tile[2 * tx][i], b = tile[2 * tx + 1][i];
+      __half* o = og + (long long)c * out_ld + r;
+      if (vec_out && r + 1 < R) {
+        *reinterpret_cast<__half2*>(o) = __halves2half2(a, b);
+      } else {
+        o[0] = a;
+        if (r + 1 < R) o[1] = b;
+      }
     }
+  }
 }
 
 // out[c] += sum_r x[r][c]
@@ -106,6 +162,12 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
                                      const float* __restrict__ gamma, float* __restrict__ dx,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
                                      float eps, int accumulate) {
+  __shared__ float s_dg[PER_LANE * 32], s_db[PER_LANE * 32];
+  for (int i = threadIdx.x; i < PER_LANE * 32; i += blockDim.x) {
+    s_dg[i] = 0.f;
+    s_db[i] = 0.f;
+  }
+  __syncthreads();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   float dg_acc[PER_LANE], db_acc[PER_LANE], gam[PER_LANE];
@@ -174,18 +236,25 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       }
     }
   }
+  // warp partials -> block partials in shared memory -> one global atomic per column per block
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     if (c < C) {
-      atomicAdd(&dgamma[c], dg_acc[i]);
-      atomicAdd(&dbeta[c], db_acc[i]);
+      atomicAdd(&s_dg[c], dg_acc[i]);
+      atomicAdd(&s_db[c], db_acc[i]);
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], s_dg[c]);
+    atomicAdd(&dbeta[c], s_db[c]);
   }
 }
 
-// softmax backward over the last dim: ds = scale * p * (dp - sum_j dp_j p_j); p given as fp16 planes
-template <int PER_LANE>
+// softmax backward over the last dim: ds = scale * p * (dp - sum_j dp_j p_j); p given as fp16 planes.
+// One warp per row; each lane owns column pairs (4-byte p loads, 8-byte dp/ds accesses); cols must be even.
+template <int PAIRS>
 __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __restrict__ dp,
                                    float* __restrict__ ds, long long rows, int cols, float scale, int terms,
                                    long long plane) {
@@ -193,28 +262,37 @@ __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  float pv[PER_LANE], dv[PER_LANE];
+  const __half2* ph = reinterpret_cast<const __half2*>(p + row * cols);
+  const __half2* pl = reinterpret_cast<const __half2*>(p + plane + row * cols);
+  const float2* dpr = reinterpret_cast<const float2*>(dp + row * cols);
+  float2* dsr = reinterpret_cast<float2*>(ds + row * cols);
+  const int npairs = cols >> 1;
+  float2 pv[PAIRS], dv[PAIRS];
   float dot = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER_LANE; ++i) {
+  for (int i = 0; i < PAIRS; ++i) {
     const int c = lane + i * 32;
-    if (c < cols) {
-      float v = __half2float(p[row * cols + c]);
-      if (terms == 2) v += __half2float(p[plane + row * cols + c]);
+    if (c < npairs) {
+      float2 v = __half22float2(ph[c]);
+      if (terms == 2) {
+        const float2 l = __half22float2(pl[c]);
+        v.x += l.x;
+        v.y += l.y;
+      }
       pv[i] = v;
-      dv[i] = dp[row * cols + c];
-      dot += v * dv[i];
+      dv[i] = dpr[c];
+      dot += v.x * dv[i].x + v.y * dv[i].y;
     } else {
-      pv[i] = 0.f;
-      dv[i] = 0.f;
+      pv[i] = make_float2(0.f, 0.f);
+      dv[i] = make_float2(0.f, 0.f);
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
 #pragma unroll
-  for (int i = 0; i < PER_LANE; ++i) {
+  for (int i = 0; i < PAIRS; ++i) {
     const int c = lane + i * 32;
-    if (c < cols) ds[row * cols + c] = scale * pv[i] * (dv[i] - dot);
+    if (c < npairs) dsr[c] = make_float2(scale * pv[i].x * (dv[i].x - dot), scale * pv[i].y * (dv[i].y - dot));
   }
 }
 
@@ -302,7 +380,7 @@ int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, 
                         t2h_stream_t stream) {
   T2H_CHECK_ARG(x && out_t && g > 0 && r > 0 && c > 0, "f32_to_planes_t: bad args");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "f32_to_planes_t: terms=%d", terms);
-  dim3 grid(ceil_div(r, 32), ceil_div(c, 32), g), block(32, 8);
+  dim3 grid(ceil_div(r, 64), ceil_div(c, 64), g), block(32, 8);
   f32_to_planes_t_kernel<<<grid, block, 0, as_stream(stream)>>>(
       x, reinterpret_cast<__half*>(out_t), reinterpret_cast<__half*>(out_n), r, c, terms, (long long)g * r * c,
       scale);
@@ -315,10 +393,15 @@ int t2h_planes_transpose(const void* x, void* out, int g, int r, int c, int64_t 
                          t2h_stream_t stream) {
   T2H_CHECK_ARG(x && out && g > 0 && r > 0 && c > 0 && ld >= c && out_ld >= r, "planes_transpose: bad args");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "planes_transpose: terms=%d", terms);
-  dim3 grid(ceil_div(r, 32), ceil_div(c, 32), g), block(32, 8);
+  T2H_CHECK_ARG((long long)g * terms <= 65535, "planes_transpose: too many groups");
+  dim3 grid(ceil_div(r, 64), ceil_div(c, 64), g * terms), block(32, 8);
+  // 4-byte accesses need even strides / offsets everywhere a half2 is formed
+  const int vec_in = (reinterpret_cast<uintptr_t>(x) % 4 == 0) && ld % 2 == 0 && g_stride % 2 == 0 && in_plane % 2 == 0;
+  const int vec_out = (reinterpret_cast<uintptr_t>(out) % 4 == 0) && out_ld % 2 == 0 && out_g_stride % 2 == 0 &&
+                      out_plane % 2 == 0;
   planes_transpose_kernel<<<grid, block, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), r, c, ld, g_stride, in_plane, terms,
-      out_ld, out_g_stride, out_plane);
+      reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), r, c, ld, g_stride, in_plane, g,
+      out_ld, out_g_stride, out_plane, vec_in, vec_out);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -350,9 +433,9 @@ int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
                       float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream) {
   T2H_CHECK_ARG(dy && x && gamma && dx && dgamma && dbeta && rows > 0 && c > 0, "layernorm_bwd: bad args");
   T2H_CHECK_ARG(c <= 1024, "layernorm_bwd: C=%d > 1024 unsupported", c);
-  const int warps = 4;
-  long long want = ceil_div64(rows, warps * 8);  // ~8 rows per warp: 8x fewer dgamma/dbeta atomics
-  const int grid = (int)(want < 1 ? 1 : want);
+  const int warps = 8;
+  long long want = ceil_div64(rows, warps * 2);  // 2 rows per warp, 16 per block: enough warps in flight to
+  const int grid = (int)(want < 1 ? 1 : want);   // cover HBM latency, 16x fewer global atomics than per-row
   cudaStream_t st = as_stream(stream);
   if (c <= 512)
     layernorm_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate);
@@ -364,16 +447,17 @@ int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
 
 int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
                     t2h_stream_t stream) {
-  T2H_CHECK_ARG(p && dp && ds && rows > 0 && cols > 0 && cols <= 2048, "softmax_bwd: bad args");
+  T2H_CHECK_ARG(p && dp && ds && rows > 0 && cols > 0 && cols <= 2048 && cols % 2 == 0,
+                "softmax_bwd: bad args (cols must be even and <= 2048)");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "softmax_bwd: terms=%d", terms);
   const int warps = 4;
   const int grid = (int)ceil_div64(rows, warps);
   cudaStream_t st = as_stream(stream);
   const __half* ph = reinterpret_cast<const __half*>(p);
   if (cols <= 512)
-    softmax_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+    softmax_bwd_kernel<8><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
   else
-    softmax_bwd_kernel<64><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+    softmax_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -55,7 +55,7 @@ def _count(n=1):
 
 def profile_tapgemm(on):
     """When on, every t2h_tapgemm launch is bracketed by CUDA events on the launching stream and
-    recorded as (algorithmic_flops, issued_flops, start_event, end_event)."""
+    recorded as (algorithmic_flops, issued_flops, start_event, end_event, (n_img, H, W, n_out, K))."""
     _PROFILE["on"] = bool(on)
     _PROFILE["records"] = []
 
@@ -90,7 +90,7 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
-             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0):
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -118,6 +118,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.residual = residual.data_ptr() if residual is not None else None
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
     p.gn_cpg = gn_cpg if gn_stats is not None else 0
+    p.k_split = k_split
     _count()
     if _PROFILE["on"]:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -126,7 +127,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
         _lib.check(lib.t2h_tapgemm(C.byref(p), _stream()))
         e1.record()
         algo = 2.0 * n_img * H * W * n_out * Cc * len(taps)
-        _PROFILE["records"].append((algo, algo * p.nterms, e0, e1))
+        _PROFILE["records"].append((algo, algo * p.nterms, e0, e1, (n_img, H, W, n_out, Cc * len(taps))))
         return
     _lib.check(lib.t2h_tapgemm(C.byref(p), _stream()))
 
@@ -263,10 +264,18 @@ def conv3x3_s2(a_ph, w, bias, *, want_stats=False):
     return out
 
 
-def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None):
+def wgrad_k_split(M, Nout, K):
+    """k-slices per output tile so that a [M,Nout] weight gradient contracted over K tokens fills the GPU"""
+    tiles = ((M + 127) // 128) * ((Nout + 255) // 256)
+    ks = min((K + 63) // 64, 148 // max(tiles, 1))
+    return ks if ks >= 2 else 0
+
+
+def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None, k_split=0):
     """a: planes [T,M,K] (any leading dims are flattened by the caller);
     w: planes [T,1,Nout,K] (pack_linear_weight).  -> fp32 [M,Nout] or planes [T,M,Nout].
-    Serves 1x1 convs on NHWC activations and nn.Linear."""
+    Serves 1x1 convs on NHWC activations and nn.Linear.  ``k_split`` >= 2 (weight gradients: small
+    output, long contraction) accumulates k-slices into a zeroed ``out``."""
     _need_cuda(a, w)
     T, M, K = a.shape
     Nout = w.shape[2]
@@ -280,7 +289,7 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
              b_sg=w.stride(0),
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
              d_strides=(0, 0, out.stride(-2), 1), d_plane=out.stride(0) if planes_out else 0,
-             bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual)
+             bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual, k_split=k_split)
     return out
 
 

@@ -205,7 +205,7 @@ class SamplerTrainer:
         dl_n, dl_t = ops.f32_to_planes_t(dlogits)                       # [Tt,M,NK], [Tt,NK,M]
         hf_t = ops.planes_transpose(hf.unsqueeze(1))[:, 0]              # [Tt,C,M]
         g_heads = self._flat_view(self.flat_g, m.head_list[0].weight, NK, C)
-        ops.linear(dl_t, hf_t.unsqueeze(1), out=g_heads)                # dW_heads = dlogits^T hf
+        self._wgrad(dl_t, hf_t, g_heads)                # dW_heads = dlogits^T hf
         d_hf = ops.linear(dl_n, w_heads[1])                             # [M, C]
         del dlogits, dl_n, dl_t
         dx = torch.zeros((M, C), dtype=torch.float32, device=x_0.device)  # running gradient of the stream
@@ -222,13 +222,13 @@ class SamplerTrainer:
             dxo_n, dxo_t = ops.f32_to_planes_t(dx)
             ops.colsum_(self.g(fc2.bias), dx)
             g_t = ops.planes_transpose(s["g"].unsqueeze(1))[:, 0]                       # [Tt,F,M]
-            ops.linear(dxo_t, g_t.unsqueeze(1), out=self.g(fc2.weight))                   # dW2 [C,F]
+            self._wgrad(dxo_t, g_t, self.g(fc2.weight))                   # dW2 [C,F]
             d_g = ops.linear(dxo_n, w["fc2"][1])                                            # [M,F]
             d_a = ops.gelu_bwd(s["pre"], d_g)
             da_n, da_t = ops.f32_to_planes_t(d_a)
             ops.colsum_(self.g(fc1.bias), d_a)
             h2_t = ops.planes_transpose(s["h2"].unsqueeze(1))[:, 0]                      # [Tt,C,M]
-            ops.linear(da_t, h2_t.unsqueeze(1), out=self.g(fc1.weight))                   # dW1 [F,C]
+            self._wgrad(da_t, h2_t, self.g(fc1.weight))                   # dW1 [F,C]
             d_h2 = ops.linear(da_n, w["fc1"][1])                                            # [M,C]
             ops.layernorm_bwd_(dx, d_h2, s["x_mid"], blk.ln2.weight.detach(), self.g(blk.ln2.weight),
                                self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True)       # dx = d x_mid
@@ -236,7 +236,7 @@ class SamplerTrainer:
             dxm_n, dxm_t = ops.f32_to_planes_t(dx)
             ops.colsum_(self.g(a.proj.bias), dx)
             y_t = ops.planes_transpose(s["y"].unsqueeze(1))[:, 0]
-            ops.linear(dxm_t, y_t.unsqueeze(1), out=self.g(a.proj.weight))                # dWp [C,C]
+            self._wgrad(dxm_t, y_t, self.g(a.proj.weight))                # dWp [C,C]
             dyv = torch.empty((Tt, M, 2 * C), dtype=torch.float16, device=dx.device)      # [d_y | v]
             ops.linear(dxm_n, w["proj"][1], planes_out=True, out=dyv[:, :, :C])            # d_y
             ops.planes_transpose(s["vt"], out=dyv.view(Tt, B, T, 2 * C)[..., C:])         # v token-major
@@ -259,12 +259,12 @@ class SamplerTrainer:
             dqk_n, dqk_t = ops.f32_to_planes_t(d_qk)
             ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 2 * C)[0], d_qk)     # [q.bias | k.bias]
             h1_t = ops.planes_transpose(s["h1"].unsqueeze(1))[:, 0]                       # [Tt,C,M]
-            ops.linear(dqk_t, h1_t.unsqueeze(1), out=self._flat_view(self.flat_g, a.query.weight, 2 * C, C))
+            self._wgrad(dqk_t, h1_t, self._flat_view(self.flat_g, a.query.weight, 2 * C, C))
             d_h1 = ops.linear(dqk_n, w["qk"][1])                                          # [M,C]
             # v projection
             dv_n, dv_t = ops.f32_to_planes_t(dv)
             ops.colsum_(self.g(a.value.bias), dv)
-            ops.linear(dv_t, h1_t.unsqueeze(1), out=self.g(a.value.weight))               # dWv [C,C]
+            self._wgrad(dv_t, h1_t, self.g(a.value.weight))               # dWv [C,C]
             d_h1 = ops.linear(dv_n, w["v"][1], residual=d_h1)
             ops.layernorm_bwd_(dx, d_h1, s["x_in"], blk.ln1.weight.detach(), self.g(blk.ln1.weight),
                                self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True)       # dx = d x_in
@@ -286,6 +286,14 @@ class SamplerTrainer:
         for h in self._handles:
             h.wait()
         self._handles = []
+
+    @staticmethod
+    def _wgrad(dy_t, x_t, out):
+        """out[n_out, n_in] = dy^T x over all tokens; dy_t [T,n_out,M], x_t [T,n_in,M] (token-contiguous
+        planes).  The output has few tiles and the contraction is long, so k-slices are spread over the SMs
+        and reduce-added into the (zeroed) gradient buffer."""
+        ops.linear(dy_t, x_t.unsqueeze(1), out=out,
+                   k_split=ops.wgrad_k_split(dy_t.shape[1], x_t.shape[1], dy_t.shape[2]))
 
     def _bucket_done(self, which, reduce):
         """gradients of a contiguous slice of the flat buffer are final: start their all-reduce (sum) now,

@@ -51,3 +51,24 @@ print(f"[{prec}] train step B={B}: {ms:.2f} ms/step, {tok / ms * 1e3:.0f} tokens
       f"{(ops.COUNTERS['launches'] - l0) // steps} launches/step, {flops / ms / 1e9:.1f} TFLOP/s algorithmic, "
       f"params {n_par / 1e6:.1f} M, loss {losses[0]:.4f} -> {float(loss):.4f}, "
       f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+
+if os.environ.get("T2H_TRAIN_PROFILE"):
+    # per-shape time of every tap-GEMM launch of one step (events around each launch; serialises nothing)
+    from collections import defaultdict
+    ops.profile_tapgemm(True)
+    e0.record()
+    tr.optimize_parameters(x_0, own, segm, tex, gen)
+    e1.record()
+    torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0, 0.0, 0.0])
+    for algo, issued, a, b, shape in ops.profile_records():
+        r = agg[shape]
+        r[0] += 1
+        r[1] += a.elapsed_time(b)
+        r[2] += issued
+    ops.profile_tapgemm(False)
+    tot = sum(r[1] for r in agg.values())
+    print(f"tapgemm total {tot:.2f} ms of {e0.elapsed_time(e1):.2f} ms step (instrumented)")
+    print(f"{'(batch, H, rows, n_out, K)':36s} {'n':>4s} {'ms':>8s} {'TF/s issued':>12s}")
+    for shape, (n, ms_, issued) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{str(shape):36s} {n:4d} {ms_:8.3f} {issued / ms_ / 1e9:12.1f}")
