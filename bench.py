@@ -185,6 +185,43 @@ def side_workloads(dev, precision):
     return out
 
 
+def train_workload(dev, precision, world, batch=16, steps=4):
+    """one optimiser step of the index-prediction transformer (q_sample masking, forward,
+    18 masked cross-entropies, backward, bucketed NCCL gradient all-reduce when world > 1, Adam), per-GPU
+    batch fixed (weak scaling).  Every rank must call this when world > 1 (collective inside)."""
+    import golden_recipes as R
+    from text2human_b200 import dist as D
+    from text2human_b200 import ops
+    from text2human_b200.transformer_arch import TransformerMultiHead
+    from text2human_b200.transformer_train import SamplerTrainer, targets_from_gt_list
+    cfg = {k: v for k, v in SAMPLER_OPT.items() if k != "sample_steps"}
+    torch.manual_seed(5)
+    net = TransformerMultiHead(**cfg).to(dev)
+    tr = SamplerTrainer(net)
+    x_0, gt_list, segm, tex = R.sampler_train_batch(6 + D.env_rank()[0], B=batch, cfg=cfg)
+    x_0, segm, tex = x_0.to(dev), segm.to(dev), tex.to(dev)
+    own = targets_from_gt_list([g.to(dev) for g in gt_list])
+    gen = torch.Generator(device=dev).manual_seed(1)
+    for _ in range(2):
+        tr.optimize_parameters(x_0, own, segm, tex, gen)
+    D.barrier()
+    torch.cuda.synchronize()
+    l0 = ops.COUNTERS["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = tr.optimize_parameters(x_0, own, segm, tex, gen)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / steps, device=dev)
+    tok = batch * 512 * world
+    flops = (6 * (24 * 12 * 512 * 512 + 18432 * 512) + 3 * 24 * 4 * 512 * 512) * tok
+    return dict(per_gpu_batch=batch, n_gpus=world, ms_per_step=ms, tokens_per_s=tok / (ms / 1e3),
+                algorithmic_tflops=flops / ms / 1e9, launches_per_step=(ops.COUNTERS["launches"] - l0) // steps,
+                precision=precision, loss=float(loss), grad_allreduce="nccl, 6 buckets overlapped with backward"
+                if world > 1 else "none (1 GPU)", params=tr.flat_p.numel())
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (PyTorch fp32, oracle port), rank 0 only."""
     if rank != 0:
@@ -258,6 +295,8 @@ def run():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-train-ddp", action="store_true",
+                    help="N>1 only: also time the sampler training step with its NCCL gradient all-reduce")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the short config-3 (hierarchy) and config-4 (sampler) side measurements")
     ap.add_argument("--graph", action="store_true",
@@ -392,6 +431,13 @@ def run():
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
         extra = side_workloads(dev, args.precision)
+        try:
+            extra["sampler_train_step"] = train_workload(dev, args.precision, 1)
+        except Exception as exc:
+            extra["sampler_train_step"] = dict(error=repr(exc))
+    if world > 1 and args.extra_train_ddp:  # opt-in: a collective runs inside (every rank takes part)
+        tw = train_workload(dev, args.precision, world)
+        extra = dict(sampler_train_step=tw) if rank == 0 else None
 
     if world > 1:
         dist.barrier()
