@@ -81,6 +81,7 @@ int t2h_device_info(int* cc_major, int* cc_minor, int* num_sms);
 
 #define T2H_ACT_NONE 0
 #define T2H_ACT_GELU 1       /* exact erf GELU, nn.GELU() transformer_arch.py:86 */
+#define T2H_ACT_RELU 2       /* ConvModule's ReLU in the index-prediction UNet / FCN head (unet_arch.py:160) */
 
 typedef struct t2h_tapgemm_params {
   /* ---- A operand (activations) ---- */
@@ -126,6 +127,8 @@ typedef struct t2h_tapgemm_params {
   double* gn_stats;      /* optional [n_img][32][2] (sum, sumsq) accumulators
                             of the fp32 output, for the following GroupNorm   */
   int32_t gn_cpg;        /* channels per group when gn_stats != NULL         */
+  int64_t bias_sn;       /* BIAS_COL with n_img > 1: element distance between the bias vectors of consecutive
+                            images (per-head biases of a batched GEMM); 0 = one shared vector          */
   int32_t k_split;       /* >= 2: split the contraction of every output tile over up to k_split CTAs whose
                             partial sums are reduce-added (TMA .add) into D, which the caller has zeroed
                             (weight gradients: few output tiles, contraction over all tokens).  Needs a
@@ -154,8 +157,10 @@ int t2h_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w,
 #define T2H_CVT_UP2X 1   /* nearest x2: F.interpolate in Upsample (vqgan_arch.py:530) */
 #define T2H_CVT_S2D 2    /* 4-phase space-to-depth for Downsample (vqgan_arch.py:547-551):
                             out[(p*2+q)][n][oh][ow][c] = x[n][2*oh+p][2*ow+q][c]  */
-/* fp32 NHWC [N,H,W,C] -> fp16 planes.  Output spatial size is (2H,2W) for UP2X,
- * (H/2,W/2) x 4 phases for S2D.  Plane layout: [terms][phases][N][h][w][C]. */
+#define T2H_CVT_MAXPOOL2 3   /* nn.MaxPool2d(2) between the index-prediction UNet's encoder stages (unet_arch.py:441) */
+#define T2H_CVT_BILINEAR2X 4 /* nn.Upsample(x2, bilinear, align_corners=False) of InterpConv (unet_arch.py:303-304) */
+/* fp32 NHWC [N,H,W,C] -> fp16 planes.  Output spatial size is (2H,2W) for UP2X / BILINEAR2X,
+ * (H/2,W/2) x 4 phases for S2D, (H/2,W/2) for MAXPOOL2.  Plane layout: [terms][phases][N][h][w][C]. */
 int t2h_f32_to_planes(const float* x, void* out, int n, int h, int w, int c,
                       int mode, int terms, t2h_stream_t stream);
 
@@ -232,6 +237,12 @@ int t2h_mask_to_ids(const float* mask, int32_t* ids, int b, int hs, int ws, int 
 /* ------------------------------------------------------------------------
  * Transformer pieces (transformer_arch.py)
  * ---------------------------------------------------------------------- */
+/* bot_index_prediction's per-position argmax (sample_model.py:199-207): logits [n_heads][rows][ncls] fp32,
+ * head[rows] = the texture id selecting the head; out[rows] = lowest index of the maximum in the row's own
+ * head, -1 where head is outside 0..n_heads-1 */
+int t2h_argmax_heads(const float* logits, const int64_t* head, int64_t* out, int64_t rows, int n_heads, int ncls,
+                     t2h_stream_t stream);
+
 /* x[b,t,:] = tok_emb[idx] + pos_emb[t] + segm_emb[segm] + tex_emb[tex]  (:251-266) fp32 */
 int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex,
                   const float* tok_emb, const float* pos_emb, const float* segm_emb,

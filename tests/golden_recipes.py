@@ -16,7 +16,8 @@ def _gen(seed, name):
 
 def fill_state_dict(spec, seed):
     """spec: iterable of (key, shape).  conv/linear/embedding weights ~ N(0, 1/fan_in) (embeddings N(0,1)*0.5),
-    biases ~ 0.1*N(0,1), norm weights 1 + 0.1*N(0,1), pos_emb/start_tok 0.02*N(0,1)."""
+    biases ~ 0.1*N(0,1), norm weights 1 + 0.1*N(0,1), pos_emb/start_tok 0.02*N(0,1); BatchNorm buffers:
+    running_mean 0.1*N(0,1), running_var U(0.5,1.5), num_batches_tracked 0."""
     sd = {}
     for key, shape in spec:
         shape = tuple(shape)
@@ -24,6 +25,12 @@ def fill_state_dict(spec, seed):
         r = torch.randn(shape, generator=g)
         leaf = key.split(".")[-1]
         parent = key.split(".")[-2] if "." in key else ""
+        if leaf == "num_batches_tracked":
+            sd[key] = torch.zeros(shape, dtype=torch.long)
+            continue
+        if leaf == "running_var":  # BatchNorm running variance: positive, around 1
+            sd[key] = (0.5 + torch.rand(shape, generator=g)).float()
+            continue
         if key in ("pos_emb", "start_tok"):
             v = 0.02 * r
         elif "emb" in parent or "embedding" in parent:
@@ -104,3 +111,13 @@ def sampler_train_batch(seed, B=2, cfg=None):
     x_0 = own + ncls * tex
     gt_list = [torch.where(tex == k, own, torch.full_like(own, -1)) for k in range(cfg["num_head"])]
     return x_0, gt_list, segm, tex
+
+
+# reduced index-prediction nets for the fixture (the real ones: UNet(in_channels=256) with base 64, and
+# MultiHeadFCNHead(in_channels=64, channels=64, num_classes=512), configs/sample_from_parsing.yml:49-58)
+TINY_UNET = dict(in_channels=32, base_channels=8)
+TINY_FCN = dict(in_channels=8, channels=8, in_index=4, num_convs=1, concat_input=False, dropout_ratio=0.1,
+                num_classes=16, align_corners=False, num_head=18)
+REAL_UNET = dict(in_channels=256)
+REAL_FCN = dict(in_channels=64, channels=64, in_index=4, num_convs=1, concat_input=False, dropout_ratio=0.1,
+                num_classes=512, align_corners=False, num_head=18)

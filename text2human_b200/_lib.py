@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libt2h.so")
 MAX_TAPS = 9
 OUT_F32, OUT_PLANES = 0, 1
 BIAS_NONE, BIAS_COL, BIAS_ROW = 0, 1, 2
-ACT_NONE, ACT_GELU = 0, 1
-CVT_PLAIN, CVT_UP2X, CVT_S2D = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+CVT_PLAIN, CVT_UP2X, CVT_S2D, CVT_MAXPOOL2, CVT_BILINEAR2X = 0, 1, 2, 3, 4
 
 
 class TapGemmParams(C.Structure):
@@ -39,7 +39,7 @@ class TapGemmParams(C.Structure):
         ("bias", C.c_void_p), ("bias_mode", C.c_int32), ("act", C.c_int32),
         ("alpha", C.c_float),
         ("residual", C.c_void_p),
-        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("k_split", C.c_int32),
+        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
     ]
 
 
@@ -67,6 +67,7 @@ SIGNATURES = {
     "t2h_onehot_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "t2h_embed_sum": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "t2h_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
+    "t2h_argmax_heads": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_f32_to_planes_t": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "t2h_planes_transpose": (_I, [_P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _P]),
     "t2h_colsum": (_I, [_P, _P, _L, _I, _P]),

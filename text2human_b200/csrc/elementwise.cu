@@ -96,8 +96,9 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ x, __half* __rest
                                      int H, int W, int C, int mode, int terms, long long plane) {
   const int c8 = C >> 3;
   int oh_n, ow_n, phases;
-  if (mode == T2H_CVT_UP2X) { oh_n = 2 * H; ow_n = 2 * W; phases = 1; }
+  if (mode == T2H_CVT_UP2X || mode == T2H_CVT_BILINEAR2X) { oh_n = 2 * H; ow_n = 2 * W; phases = 1; }
   else if (mode == T2H_CVT_S2D) { oh_n = H / 2; ow_n = W / 2; phases = 4; }
+  else if (mode == T2H_CVT_MAXPOOL2) { oh_n = H / 2; ow_n = W / 2; phases = 1; }
   else { oh_n = H; ow_n = W; phases = 1; }
   const long long total = (long long)phases * N * oh_n * ow_n * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -108,6 +109,42 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ x, __half* __rest
     const int oh = (int)(r % oh_n); r /= oh_n;
     const int n = (int)(r % N);
     const int ph = (int)(r / N);
+    if (mode == T2H_CVT_MAXPOOL2) {
+      // nn.MaxPool2d(2): window rows 2oh..2oh+1, cols 2ow..2ow+1 (odd trailing row/column dropped)
+      const float* b = x + (((long long)n * H + 2 * oh) * W + 2 * ow) * C + cc * 8;
+      float f[8], g[8];
+      load8(b, f);
+      load8(b + C, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], g[k]);
+      load8(b + (long long)W * C, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], g[k]);
+      load8(b + (long long)W * C + C, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], g[k]);
+      store_split8(f, out, i * 8, plane, terms);
+      continue;
+    }
+    if (mode == T2H_CVT_BILINEAR2X) {
+      // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False): src = (dst + 0.5) / 2 - 0.5,
+      // clamped at 0; neighbours clamped at the border
+      const float sh = fmaxf(0.5f * (oh + 0.5f) - 0.5f, 0.f), sw = fmaxf(0.5f * (ow + 0.5f) - 0.5f, 0.f);
+      const int h0 = (int)sh, w0 = (int)sw;
+      const int h1 = min(h0 + 1, H - 1), w1 = min(w0 + 1, W - 1);
+      const float lh = sh - h0, lw = sw - w0;
+      const float* b = x + (long long)n * H * W * C + cc * 8;
+      float v00[8], v01[8], v10[8], v11[8], f[8];
+      load8(b + ((long long)h0 * W + w0) * C, v00);
+      load8(b + ((long long)h0 * W + w1) * C, v01);
+      load8(b + ((long long)h1 * W + w0) * C, v10);
+      load8(b + ((long long)h1 * W + w1) * C, v11);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        f[k] = (1.f - lh) * ((1.f - lw) * v00[k] + lw * v01[k]) + lh * ((1.f - lw) * v10[k] + lw * v11[k]);
+      store_split8(f, out, i * 8, plane, terms);
+      continue;
+    }
     int ih, iw;
     if (mode == T2H_CVT_UP2X) { ih = oh >> 1; iw = ow >> 1; }
     else if (mode == T2H_CVT_S2D) { ih = 2 * oh + (ph >> 1); iw = 2 * ow + (ph & 1); }
@@ -384,6 +421,42 @@ static inline int grid_for(long long work, int block) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+
+// Per-row argmax inside the row's own head (bot_index_prediction, sample_model.py:183-213):
+// logits [G][M][ncls]; row m reads head[m]'s slice and returns the lowest index of the maximum (-1 when
+// head[m] is outside 0..G-1).  One warp per row.
+__global__ void argmax_heads_kernel(const float* __restrict__ logits, const long long* __restrict__ head,
+                                    long long* __restrict__ out, long long M, int G, int ncls) {
+  const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  const long long hd = head[m];
+  if (hd < 0 || hd >= G) {
+    if (lane == 0) out[m] = -1;
+    return;
+  }
+  const float* row = logits + ((long long)hd * M + m) * ncls;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < ncls; c += 32) {
+    const float v = row[c];
+    if (v > best) {  // strictly greater: within a lane the lowest index of the maximum is kept
+      best = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) out[m] = bi == 0x7fffffff ? 0 : bi;
+}
+
 }  // namespace t2h
 
 using namespace t2h;
@@ -426,11 +499,13 @@ int t2h_f32_to_planes(const float* x, void* out, int n, int h, int w, int c, int
                       t2h_stream_t stream) {
   T2H_CHECK_ARG(x && out && n > 0 && h > 0 && w > 0 && c > 0, "f32_to_planes: bad shape");
   T2H_CHECK_ARG(c % 8 == 0, "f32_to_planes: C=%d must be a multiple of 8", c);
-  T2H_CHECK_ARG(mode >= 0 && mode <= 2, "f32_to_planes: mode=%d", mode);
+  T2H_CHECK_ARG(mode >= 0 && mode <= 4, "f32_to_planes: mode=%d", mode);
   T2H_CHECK_ARG(mode != T2H_CVT_S2D || (h % 2 == 0 && w % 2 == 0), "f32_to_planes: S2D needs even H,W");
+  T2H_CHECK_ARG(mode != T2H_CVT_MAXPOOL2 || (h >= 2 && w >= 2), "f32_to_planes: MAXPOOL2 needs H,W >= 2");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "f32_to_planes: terms=%d", terms);
   long long out_elems = (long long)n * h * w * c;
-  if (mode == T2H_CVT_UP2X) out_elems *= 4;
+  if (mode == T2H_CVT_UP2X || mode == T2H_CVT_BILINEAR2X) out_elems *= 4;
+  if (mode == T2H_CVT_MAXPOOL2) out_elems = (long long)n * (h / 2) * (w / 2) * c;
   const long long work = out_elems / 8;
   f32_to_planes_kernel<<<grid_for(work, 256), 256, 0, as_stream(stream)>>>(
       x, reinterpret_cast<__half*>(out), n, h, w, c, mode, terms, out_elems);
@@ -554,6 +629,16 @@ int t2h_mask_to_ids(const float* mask, int32_t* ids, int b, int hs, int ws, int 
   T2H_CHECK_ARG(mask && ids && b > 0 && hs > 0 && ws > 0 && ht > 0 && wt > 0, "mask_to_ids: bad args");
   const long long total = (long long)b * ht * wt;
   mask_to_ids_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(mask, ids, b, hs, ws, ht, wt);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_argmax_heads(const float* logits, const int64_t* head, int64_t* out, int64_t rows, int n_heads, int ncls,
+                     t2h_stream_t stream) {
+  T2H_CHECK_ARG(logits && head && out && rows > 0 && n_heads > 0 && ncls > 0, "argmax_heads: bad args");
+  const int warps = 8;
+  argmax_heads_kernel<<<(unsigned)ceil_div64(rows, warps), warps * 32, 0, as_stream(stream)>>>(
+      logits, reinterpret_cast<const long long*>(head), reinterpret_cast<long long*>(out), rows, n_heads, ncls);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -46,6 +46,7 @@ struct TapGemmDev {
   int d_mode, d_terms, epi_mode, d_term_imgs;
   long long d_plane, d_sn, d_sh, d_sw, d_sc;
   const float* bias;
+  long long bias_sn;  // BIAS_COL: elements between the bias vectors of consecutive images (0 = shared)
   int bias_mode, act;
   float alpha;
   const float* residual;
@@ -423,7 +424,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               if (col0 + i < P.n_out) {  // n_out % 4 == 0 in this mode
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + col0 + i));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + t.img * P.bias_sn + col0 + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
             }
@@ -431,6 +432,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (P.act == T2H_ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (P.act == T2H_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (has_res) {
             mbar_wait(&res_bar[buf], res_par[buf]);
@@ -523,7 +527,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < 32; i += 4) {
                 if (col0 + half * 32 + i < P.n_out) {  // n_out % 8 == 0 in this mode
                   const float4 b4 =
-                      __ldg(reinterpret_cast<const float4*>(P.bias + col0 + half * 32 + i));
+                      __ldg(reinterpret_cast<const float4*>(P.bias + t.img * P.bias_sn + col0 + half * 32 + i));
                   v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                 }
               }
@@ -531,6 +535,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (P.act == T2H_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            } else if (P.act == T2H_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -584,11 +591,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (P.bias_mode == T2H_BIAS_COL) {
 #pragma unroll
               for (int i = 0; i < CH; ++i)
-                if (col0 + i < P.n_out) v[i] += __ldg(P.bias + col0 + i);
+                if (col0 + i < P.n_out) v[i] += __ldg(P.bias + t.img * P.bias_sn + col0 + i);
             }
             if (P.act == T2H_ACT_GELU) {
 #pragma unroll
               for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+            } else if (P.act == T2H_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
             }
             if (P.d_mode == T2H_OUT_F32) {
               float* dst = reinterpret_cast<float*>(P.d);
@@ -787,7 +797,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   P.b_term_g = p->b_term_g; P.b_batched = p->b_batched; P.b_batched_h = p->b_batched_h;
   P.d = p->d; P.d_mode = p->d_mode; P.d_terms = p->d_terms; P.d_plane = p->d_plane;
   P.d_sn = p->d_sn; P.d_sh = p->d_sh; P.d_sw = p->d_sw; P.d_sc = p->d_sc;
-  P.bias = p->bias; P.bias_mode = p->bias_mode; P.act = p->act; P.alpha = p->alpha;
+  P.bias = p->bias; P.bias_sn = p->bias_mode == T2H_BIAS_COL ? p->bias_sn : 0; P.bias_mode = p->bias_mode; P.act = p->act; P.alpha = p->alpha;
   P.residual = p->residual; P.gn_stats = p->gn_stats; P.gn_cpg = p->gn_cpg;
   P.gn_groups = p->gn_cpg > 0 ? p->n_out / p->gn_cpg : 0;
   P.d_term_imgs = 0;
@@ -896,7 +906,8 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     tma_ok = tma_ok && sn > 0 && p->d_plane % sn == 0 && p->d_plane % align_el == 0;
   }
   if (p->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->residual) % 16 == 0);
-  if (p->bias_mode == T2H_BIAS_COL) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0);
+  if (p->bias_mode == T2H_BIAS_COL)
+    tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0) && p->bias_sn % 4 == 0;
   P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
   if (swap) P.epi_mode = swap_direct ? EPI_DIRECT : EPI_TMA_F32;
   // ---- split-K: k-slices of one tile go to different CTAs and are reduce-added into a zeroed output

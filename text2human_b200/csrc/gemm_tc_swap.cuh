@@ -243,7 +243,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
       const int c0 = t.n0 + q * 32;  // this warp's first output channel
       const float bias_c =
-          (P.bias_mode == T2H_BIAS_COL && c0 + lane < P.n_out) ? __ldg(P.bias + c0 + lane) : 0.f;
+          (P.bias_mode == T2H_BIAS_COL && c0 + lane < P.n_out) ? __ldg(P.bias + t.img * P.bias_sn + c0 + lane) : 0.f;
       auto issue_res = [&](int k) {
         mbar_expect_tx(&res_bar[e], kWarpTile);
         tma_load_4d(&tmR, &res_bar[e], my_res, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
@@ -280,6 +280,9 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (P.act == T2H_ACT_GELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        } else if (P.act == T2H_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (has_res) {
           mbar_wait(&res_bar[e], res_par);

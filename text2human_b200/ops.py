@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, BIAS_COL, BIAS_NONE, BIAS_ROW, CVT_PLAIN, CVT_S2D, CVT_UP2X,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, CVT_BILINEAR2X, CVT_MAXPOOL2, BIAS_COL, BIAS_NONE, BIAS_ROW, CVT_PLAIN, CVT_S2D, CVT_UP2X,
                    OUT_F32, OUT_PLANES, TapGemmParams)
 
 # ----------------------------------------------------------------------------
@@ -90,7 +90,7 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
-             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0):
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -119,6 +119,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
     p.gn_cpg = gn_cpg if gn_stats is not None else 0
     p.k_split = k_split
+    p.bias_sn = bias_sn
     _count()
     if _PROFILE["on"]:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -154,7 +155,8 @@ def _stats_for(cout, n, device, want):
     return new_gn_stats(n, device), cpg
 
 
-def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False, want_stats=False, taps=None):
+def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False, want_stats=False, taps=None,
+            act=ACT_NONE):
     """3x3 stride-1 pad-1 conv (or, with taps=_TAPS_1 and a [T,1,Cout,C] weight, a 1x1 conv).
     a: planes [T,N,H,W,C]; w: packed planes [T,ntaps,Cout,C] (see pack_conv_weight); bias fp32 [Cout].
     Returns fp32 NHWC [N,H,W,Cout] (or NCHW with nchw_out) or planes [T,N,H,W,Cout]; with
@@ -177,7 +179,7 @@ def conv3x3(a, w, bias, *, residual=None, planes_out=False, nchw_out=False, want
              b_sg=Cout * Cc,
              taps=taps, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
              d_plane=N * H * W * Cout, bias=bias, bias_mode=BIAS_COL, residual=residual,
-             gn_stats=stats, gn_cpg=cpg)
+             gn_stats=stats, gn_cpg=cpg, act=act)
     if want_stats:
         return out, stats
     return out
@@ -293,10 +295,10 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
     return out
 
 
-def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False):
+def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False, bias_col=None, act=ACT_NONE):
     """out[g] = a[g] @ b[g]^T.  a: planes [T,G,M,K] (or [T,1,M,K] with a_bcast);
     b: planes [T,G,N,K]; views with a unit last stride are accepted.
-    -> fp32 [G,M,N] or planes [T,G,M,N]."""
+    -> fp32 [G,M,N] or planes [T,G,M,N].  bias_row fp32 [M] (shared) or bias_col fp32 [G,N] (per group)."""
     _need_cuda(a, b)
     T, Ga, M, K = a.shape
     Tb, G, N, Kb = b.shape
@@ -312,7 +314,9 @@ def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False):
              n_out=N, b_sn=b.stride(2),
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
              d_strides=(M * N, 0, N, 1), d_plane=G * M * N,
-             bias=bias_row, bias_mode=BIAS_ROW, alpha=alpha)
+             bias=bias_row if bias_col is None else bias_col,
+             bias_mode=BIAS_ROW if bias_col is None else BIAS_COL,
+             bias_sn=0 if bias_col is None else N, alpha=alpha, act=act)
     return out
 
 
@@ -423,13 +427,15 @@ def nchw_to_nhwc(x):
 
 
 def f32_to_planes(x, mode=CVT_PLAIN, terms=None):
-    """fp32 NHWC [N,H,W,C] -> planes.  PLAIN: [T,N,H,W,C]; UP2X: [T,N,2H,2W,C];
-    S2D: [T,4,N,H/2,W/2,C]."""
+    """fp32 NHWC [N,H,W,C] -> planes.  PLAIN: [T,N,H,W,C]; UP2X (nearest) / BILINEAR2X: [T,N,2H,2W,C];
+    S2D: [T,4,N,H/2,W/2,C]; MAXPOOL2: [T,N,H/2,W/2,C]."""
     _need_cuda(x)
     N, H, W, Cc = x.shape
     terms = terms or get_terms()
-    if mode == CVT_UP2X:
+    if mode in (CVT_UP2X, CVT_BILINEAR2X):
         shape = (terms, N, 2 * H, 2 * W, Cc)
+    elif mode == CVT_MAXPOOL2:
+        shape = (terms, N, H // 2, W // 2, Cc)
     elif mode == CVT_S2D:
         shape = (terms, 4, N, H // 2, W // 2, Cc)
     else:
@@ -676,3 +682,18 @@ def adam_(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _count(1)
     _lib.check(_lib.load().t2h_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps, step,
                                     grad_scale, _stream()))
+
+
+# ----------------------------------------------------------------------------
+# index prediction (UNet + multi-head FCN) helpers
+# ----------------------------------------------------------------------------
+def argmax_heads(logits, head):
+    """logits fp32 [G, M, ncls]; head int64 [M] -> int64 [M]: argmax (lowest index on ties) inside each row's
+    own head, -1 where head is outside 0..G-1"""
+    _need_cuda(logits, head)
+    G, M, ncls = logits.shape
+    assert logits.is_contiguous() and head.numel() == M and head.dtype == torch.int64
+    out = torch.empty((M,), dtype=torch.int64, device=logits.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_argmax_heads(_ptr(logits), _ptr(head.contiguous()), _ptr(out), M, G, ncls, _stream()))
+    return out

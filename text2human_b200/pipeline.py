@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .index_pred_arch import MultiHeadFCNHead, UNet, bot_index_prediction
 from .transformer_arch import TransformerMultiHead
 from .vqgan_arch import (Decoder, DecoderRes, Encoder, VectorQuantizer, VectorQuantizerSpatialTextureAware,
                          VectorQuantizerTexture, conv1x1_nhwc)
@@ -277,3 +278,75 @@ class Sampler(nn.Module):
         final = torch.where(unmasked & valid_tex, x_t - 1024 * tex_c, torch.full_like(x_t, -1))
         out = [torch.where(tex == k, final, torch.full_like(final, -1)) for k in range(nh)]
         return out, x_t
+
+
+class SampleFromParsingModel(nn.Module):
+    """parsing map + texture mask -> image: the whole of ``BaseSampleModel.sample_and_refine``
+    (sample_model.py:215-254) with the reference's component names and ``opt`` keys
+    (configs/sample_from_parsing.yml): segm tokenizer -> diffusion sampler -> top codebook gather ->
+    index-prediction UNet/FCN -> bottom codebook gather -> DecoderRes -> Decoder.  The reference decodes one
+    sample at a time; here the whole batch goes through every stage at once."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.decoder = Decoder(in_channels=opt['top_in_channels'], resolution=opt['top_resolution'],
+                               z_channels=opt['top_z_channels'], ch=opt['top_ch'], out_ch=opt['top_out_ch'],
+                               num_res_blocks=opt['top_num_res_blocks'],
+                               attn_resolutions=opt['top_attn_resolutions'], ch_mult=opt['top_ch_mult'],
+                               dropout=opt['top_dropout'], resamp_with_conv=True, give_pre_end=False)
+        self.top_quantize = VectorQuantizerTexture(1024, opt['embed_dim'], beta=0.25)
+        self.top_post_quant_conv = torch.nn.Conv2d(opt['embed_dim'], opt["top_z_channels"], 1)
+        self.bot_decoder_res = DecoderRes(in_channels=opt['bot_in_channels'], resolution=opt['bot_resolution'],
+                                          z_channels=opt['bot_z_channels'], ch=opt['bot_ch'],
+                                          num_res_blocks=opt['bot_num_res_blocks'], ch_mult=opt['bot_ch_mult'],
+                                          dropout=opt['bot_dropout'], give_pre_end=False)
+        self.bot_quantize = VectorQuantizerSpatialTextureAware(
+            opt['bot_n_embed'], opt['embed_dim'], beta=0.25, spatial_size=opt['bot_codebook_spatial_size'])
+        self.bot_post_quant_conv = torch.nn.Conv2d(opt['embed_dim'], opt["bot_z_channels"], 1)
+        self.index_pred_guidance_encoder = UNet(in_channels=opt['index_pred_encoder_in_channels'])
+        self.index_pred_decoder = MultiHeadFCNHead(
+            in_channels=opt['index_pred_fc_in_channels'], in_index=opt['index_pred_fc_in_index'],
+            channels=opt['index_pred_fc_channels'], num_convs=opt['index_pred_fc_num_convs'],
+            concat_input=opt['index_pred_fc_concat_input'], dropout_ratio=opt['index_pred_fc_dropout_ratio'],
+            num_classes=opt['index_pred_fc_num_classes'], align_corners=opt['index_pred_fc_align_corners'],
+            num_head=18)
+        self.segm = SegmTokenizer(opt)
+        self.sampler = Sampler(opt)
+        self.shape = tuple(opt['latent_shape'])
+
+    @property
+    def sampler_fn(self):
+        return self.sampler.sampler_fn
+
+    @torch.no_grad()
+    def bot_index_prediction(self, feature_top, texture_mask):
+        """feature_top fp32 NCHW [B,256,32,16] -> 18 int64 maps [B,32,16] (-1 outside each texture)"""
+        return bot_index_prediction(self.index_pred_guidance_encoder, self.index_pred_decoder, feature_top,
+                                    texture_mask, self.shape)
+
+    @torch.no_grad()
+    def decode_top_tokens(self, top_list, texture_mask):
+        """sampled top tokens -> image in [0,1] (sample_model.py:225-246, batched)"""
+        B = texture_mask.shape[0]
+        h, w = self.shape
+        zt = self.top_quantize.get_codebook_entry(top_list, texture_mask, (B, h, w, self.opt["top_z_channels"]),
+                                                  nhwc=True)
+        quant_top = conv1x1_nhwc(zt, self.top_post_quant_conv)
+        own, _ = bot_index_prediction(self.index_pred_guidance_encoder, self.index_pred_decoder, quant_top,
+                                      texture_mask, self.shape, as_list=False, nhwc_in=True)
+        zb = self.bot_quantize.get_codebook_entry(own, texture_mask, (B, h, w, self.opt["bot_z_channels"]),
+                                                  nhwc=True)
+        res = self.bot_decoder_res.forward_nhwc(conv1x1_nhwc(zb, self.bot_post_quant_conv))
+        dec = self.decoder.forward_nhwc(quant_top, bot_h=res)
+        return dec.add_(1.0).mul_(0.5).clamp_(0, 1)
+
+    @torch.no_grad()
+    def sample_and_refine(self, segm, texture_mask, temp=1.0, sample_steps=None, generator=None):
+        """segm [B,1,H,W] parsing ids, texture_mask [B,1,H,W] texture ids -> images [B,3,512,256] in [0,1]"""
+        B = segm.shape[0]
+        segm_tokens = self.segm.get_quantized_segm(segm).view(B, -1)
+        top_list, _ = self.sampler.sample_fn(segm_tokens, texture_mask, temp=temp, sample_steps=sample_steps,
+                                             generator=generator)
+        h, w = self.shape
+        return self.decode_top_tokens([t.view(B, h, w) for t in top_list], texture_mask)

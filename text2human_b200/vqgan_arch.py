@@ -546,7 +546,10 @@ class _TextureQuantizerBase(nn.Module):
         return _cached(self, ("cb",), ws, lambda: torch.stack([w.detach().float() for w in ws]).contiguous())
 
     def _resolve_indices(self, indices_list, ids):
-        """pick, per position, the entry of the list its texture id selects (reference :297-303)"""
+        """pick, per position, the entry of the list its texture id selects (reference :297-303); a single
+        tensor is taken as the already-resolved own-codebook index map"""
+        if torch.is_tensor(indices_list):
+            return indices_list.reshape(ids.shape)
         stacked = torch.stack([i.reshape(ids.shape) for i in indices_list])  # [18,B,h,w]
         sel = ids.clamp(0, self.NUM_BOOKS - 1).long().unsqueeze(0)
         return stacked.gather(0, sel).squeeze(0)
