@@ -268,3 +268,38 @@ def test_training_reduces_loss_at_the_real_sampler_shape():
     # optimize_parameters draws its own t and mask like the reference
     loss, vb = tr.optimize_parameters(x_0, own, segm, tex)
     assert math.isfinite(float(loss)) and math.isfinite(float(vb))
+
+
+def test_training_wrapper_feed_data_and_step():
+    """TransformerTextureAwareModel.feed_data (frozen tokenizers -> tokens, transformer_model.py:273-288) +
+    optimize_parameters, real tokenizer sizes (configs/sampler.yml), 2 transformer layers"""
+    import contextlib
+    import io
+    from text2human_b200.pipeline import TransformerTextureAwareModel
+    _ops()
+    opt = dict(img_ch=128, img_num_res_blocks=2, img_attn_resolutions=[32], img_ch_mult=[1, 1, 2, 2, 4],
+               img_in_channels=3, img_resolution=512, img_z_channels=256, img_double_z=False, img_dropout=0.0,
+               img_n_embed=1024, img_embed_dim=256, img_out_ch=3,
+               segm_double_z=False, segm_z_channels=32, segm_resolution=512, segm_in_channels=24, segm_out_ch=24,
+               segm_ch=64, segm_ch_mult=[1, 1, 2, 2, 4], segm_num_res_blocks=1, segm_attn_resolutions=[16],
+               segm_dropout=0.0, segm_num_segm_classes=24, segm_n_embed=1024, segm_embed_dim=32,
+               codebook_size=18432, segm_codebook_size=1024, texture_codebook_size=18, bert_n_emb=512,
+               bert_n_layers=2, bert_n_head=8, block_size=512, latent_shape=[32, 16], embd_pdrop=0.0,
+               resid_pdrop=0.0, attn_pdrop=0.0, num_head=18, loss_type="reweighted_elbo", lr=1e-4)
+    torch.manual_seed(7)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TransformerTextureAwareModel(opt).to(DEV)
+    B = 2
+    data = dict(image=R.image(1, B, 3, 512, 256), segm=R.blocky_mask(2, B, 512, 256, 16, n_ids=24),
+                texture_mask=R.blocky_mask(3, B, 512, 256, 32))
+    m.feed_data(data)
+    tex = F.interpolate(data["texture_mask"], (32, 16), mode="nearest").view(B, -1).long().to(DEV)
+    assert torch.equal(m.texture_tokens, tex)
+    assert m.input_indices.shape == (B, 512) and torch.equal(m.input_indices, m.gt_own + 1024 * tex)
+    assert int(m.gt_own.min()) >= 0 and int(m.gt_own.max()) < 1024
+    assert m.segm_tokens.shape == (B, 512) and int(m.segm_tokens.max()) < 1024
+    g = torch.Generator(device=DEV).manual_seed(3)
+    l0, _ = m.optimize_parameters(g)
+    l1, vb = m.optimize_parameters(g)
+    assert math.isfinite(float(l0)) and math.isfinite(float(l1)) and math.isfinite(float(vb))
+    assert m.trainer.step_count == 2

@@ -350,3 +350,62 @@ class SampleFromParsingModel(nn.Module):
                                              generator=generator)
         h, w = self.shape
         return self.decode_top_tokens([t.view(B, h, w) for t in top_list], texture_mask)
+
+
+class TransformerTextureAwareModel(nn.Module):
+    """The sampler's training wrapper (reference models/transformer_model.py:18-303) with its component names
+    and ``opt`` keys (configs/sampler.yml): frozen image tokenizer (top Encoder + VectorQuantizerTexture), frozen
+    segm tokenizer, and the trainable ``_denoise_fn`` driven by ``SamplerTrainer``."""
+
+    def __init__(self, opt):
+        super().__init__()
+        from .transformer_train import SamplerTrainer
+        self.opt = opt
+        self.img_encoder = Encoder(ch=opt['img_ch'], num_res_blocks=opt['img_num_res_blocks'],
+                                   attn_resolutions=opt['img_attn_resolutions'], ch_mult=opt['img_ch_mult'],
+                                   in_channels=opt['img_in_channels'], resolution=opt['img_resolution'],
+                                   z_channels=opt['img_z_channels'], double_z=opt['img_double_z'],
+                                   dropout=opt['img_dropout'])
+        self.img_quantizer = VectorQuantizerTexture(opt['img_n_embed'], opt['img_embed_dim'], beta=0.25)
+        self.img_quant_conv = torch.nn.Conv2d(opt["img_z_channels"], opt['img_embed_dim'], 1)
+        self.segm = SegmTokenizer(opt)
+        self._denoise_fn = TransformerMultiHead(
+            codebook_size=opt['codebook_size'], segm_codebook_size=opt['segm_codebook_size'],
+            texture_codebook_size=opt['texture_codebook_size'], bert_n_emb=opt['bert_n_emb'],
+            bert_n_layers=opt['bert_n_layers'], bert_n_head=opt['bert_n_head'], block_size=opt['block_size'],
+            latent_shape=opt['latent_shape'], embd_pdrop=opt['embd_pdrop'], resid_pdrop=opt['resid_pdrop'],
+            attn_pdrop=opt['attn_pdrop'], num_head=opt['num_head'])
+        self.shape = tuple(opt['latent_shape'])
+        self.num_timesteps = 1000
+        self._trainer_cls = SamplerTrainer
+        self.trainer = None
+        self.log_dict = {}
+
+    @torch.no_grad()
+    def get_quantized_img(self, image, texture_mask):
+        """-> (continual tokens [B,T], own-codebook targets [B,T], texture ids [B,T]); the reference returns the
+        targets as 18 lists with -1 fills (:154-170), of which each position uses exactly one"""
+        B = image.shape[0]
+        z = conv1x1_nhwc(self.img_encoder.forward_nhwc(ops.nchw_to_nhwc(image)), self.img_quant_conv)
+        r = self.img_quantizer.forward_nhwc(z, texture_mask)
+        return r["idx_cont"].view(B, -1), r["idx"].view(B, -1), r["ids"].view(B, -1).long()
+
+    @torch.no_grad()
+    def feed_data(self, data):
+        """data: {'image' [B,3,H,W], 'segm' [B,1,H,W], 'texture_mask' [B,1,H,W]} (reference :273-288)"""
+        dev = next(self._denoise_fn.parameters()).device
+        image, segm, tm = data['image'].to(dev), data['segm'].to(dev), data['texture_mask'].to(dev)
+        self.input_indices, self.gt_own, _ = self.get_quantized_img(image, tm)
+        B = image.shape[0]
+        self.texture_tokens = ops.mask_to_ids(tm, self.shape[0], self.shape[1]).view(B, -1).long()
+        self.segm_tokens = self.segm.get_quantized_segm(segm).view(B, -1)
+
+    def optimize_parameters(self, generator=None):
+        if self.trainer is None:
+            self.trainer = self._trainer_cls(self._denoise_fn, lr=self.opt.get('lr', 1e-4),
+                                             num_timesteps=self.num_timesteps,
+                                             loss_type=self.opt.get('loss_type', 'reweighted_elbo'))
+        loss, vb = self.trainer.optimize_parameters(self.input_indices, self.gt_own, self.segm_tokens,
+                                                    self.texture_tokens.clamp(0, 17), generator)
+        self.log_dict['loss'], self.log_dict['vb_loss'] = loss, vb
+        return loss, vb
