@@ -129,10 +129,12 @@ typedef struct t2h_tapgemm_params {
   int32_t gn_cpg;        /* channels per group when gn_stats != NULL         */
   int64_t bias_sn;       /* BIAS_COL with n_img > 1: element distance between the bias vectors of consecutive
                             images (per-head biases of a batched GEMM); 0 = one shared vector          */
-  int32_t k_split;       /* >= 2: split the contraction of every output tile over up to k_split CTAs whose
-                            partial sums are reduce-added (TMA .add) into D, which the caller has zeroed
-                            (weight gradients: few output tiles, contraction over all tokens).  Needs a
-                            16-byte-aligned fp32 D and no bias/act/residual/gn_stats.  0/1: off        */
+  int32_t k_split;       /* >= 2: D += alpha*A.B (+ column bias, once): the contraction of every output tile
+                            is split over up to k_split CTAs whose partial sums are reduce-added (TMA .add)
+                            into the existing contents of D -- a zeroed gradient buffer (weight gradients:
+                            few output tiles, contraction over all tokens) or the residual stream itself
+                            (x += proj(y) at small batch).  Needs a 16-byte-aligned fp32 D and no row bias /
+                            act / residual / gn_stats.  0/1: off (D is overwritten)                     */
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);

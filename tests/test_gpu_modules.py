@@ -238,8 +238,15 @@ def test_sampler_transformer_logits_and_sampling_loop(cuda, mode):
     got = s.sampler_fn.forward_logits(idx, segm, tex)
     assert got.shape == (B, T, 18, 1024)
     assert _rel(got, want) < _tol(mode)
-    lst = s.sampler_fn(idx, segm, tex)
+    lst = s.sampler_fn(idx, segm, tex)   # deterministic by default: a second forward is bit-identical
     assert len(lst) == 18 and lst[3].shape == (B, T, 1024) and torch.equal(lst[3], got[:, :, 3])
+    from text2human_b200 import ops
+    old = ops.set_split_k(inference=True)   # opt-in small-batch path: k-slices reduce-added into the stream
+    try:
+        got_sk = s.sampler_fn.forward_logits(idx, segm, tex)
+    finally:
+        ops.set_split_k(**old)
+    assert _rel(got_sk, want) < _tol(mode) and _rel(got_sk, got) < 1e-4
     if mode == "fp32":
         mask = R.blocky_mask(4, B, 512, 256, 64).to(cuda)
         gen = torch.Generator(device=cuda).manual_seed(2021)

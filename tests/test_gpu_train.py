@@ -72,8 +72,14 @@ def test_split_k_weight_gradient_gemm(M, N, K):
     assert _rel(out, plain) < 1e-4                                 # only the accumulation order differs
     ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)       # accumulates: twice the gradient
     assert _rel(out, 2 * plain) < 1e-4
+    # in-place residual accumulate with a column bias (x += lin(a), the small-batch proj / fc2 path)
+    base = torch.randn(M, N, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    acc = base.clone()
+    ops.linear(dy_t, x_t.unsqueeze(1), bias, out=acc, k_split=ks)
+    assert _rel(acc, base.double() + want + bias.double()) < 1e-4
     with pytest.raises(Exception):
-        ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks, bias=torch.zeros(N, device=DEV))
+        ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks, residual=base)
 
 
 def test_colsum_gelu_layernorm_softmax_backward_kernels():

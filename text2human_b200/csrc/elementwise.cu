@@ -268,6 +268,8 @@ template <int PER_LANE>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ out,
                                     long long rows, int cols, float scale, int terms,
                                     long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();  // before any early return: a grid none of whose CTAs wait could finish before its predecessor
   const int warps = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -311,6 +313,8 @@ template <int PER_LANE>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ out,
                                  long long rows, int C, float eps, int terms, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();  // before any early return: a grid none of whose CTAs wait could finish before its predecessor
   const int warps = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -355,6 +359,8 @@ __global__ void embed_sum_kernel(const long long* __restrict__ idx, const long l
                                  const float* __restrict__ pos_emb, const float* __restrict__ segm_emb,
                                  const float* __restrict__ tex_emb, float* __restrict__ x, int T,
                                  int C) {
+  pdl_launch_dependents();
+  pdl_wait();  // before any early return: a grid none of whose CTAs wait could finish before its predecessor
   const long long row = blockIdx.x;  // b*T + t
   const int t = (int)(row % T);
   const float4* a = reinterpret_cast<const float4*>(tok_emb + idx[row] * C);
@@ -575,9 +581,9 @@ int t2h_softmax_rows(const float* s, void* out, int64_t rows, int cols, float sc
   const long long plane = rows * cols;
   cudaStream_t st = as_stream(stream);
   if (cols <= 512)
-    softmax_rows_kernel<16><<<grid, warps * 32, 0, st>>>(s, o, rows, cols, scale, terms, plane);
+    T2H_CUDA(launch_pdl(softmax_rows_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, s, o, rows, cols, scale, terms, plane));
   else
-    softmax_rows_kernel<64><<<grid, warps * 32, 0, st>>>(s, o, rows, cols, scale, terms, plane);
+    T2H_CUDA(launch_pdl(softmax_rows_kernel<64>, dim3(grid), dim3(warps * 32), 0, st, s, o, rows, cols, scale, terms, plane));
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -593,9 +599,9 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
   const long long plane = rows * c;
   cudaStream_t st = as_stream(stream);
   if (c <= 512)
-    layernorm_kernel<16><<<grid, warps * 32, 0, st>>>(x, gamma, beta, o, rows, c, eps, terms, plane);
+    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, o, rows, c, eps, terms, plane));
   else
-    layernorm_kernel<32><<<grid, warps * 32, 0, st>>>(x, gamma, beta, o, rows, c, eps, terms, plane);
+    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, o, rows, c, eps, terms, plane));
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -605,10 +611,9 @@ int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex, c
                   int t, int c, t2h_stream_t stream) {
   T2H_CHECK_ARG(idx && segm && tex && tok_emb && pos_emb && segm_emb && tex_emb && x, "embed_sum: null");
   T2H_CHECK_ARG(b > 0 && t > 0 && c > 0 && c % 4 == 0, "embed_sum: bad shape");
-  embed_sum_kernel<<<b * t, 128, 0, as_stream(stream)>>>(
-      reinterpret_cast<const long long*>(idx), reinterpret_cast<const long long*>(segm),
-      reinterpret_cast<const long long*>(tex), tok_emb, pos_emb, segm_emb, tex_emb, x, t, c);
-  T2H_LAUNCH_OK();
+  T2H_CUDA(launch_pdl(embed_sum_kernel, dim3(b * t), dim3(128), 0, as_stream(stream),
+                      reinterpret_cast<const long long*>(idx), reinterpret_cast<const long long*>(segm),
+                      reinterpret_cast<const long long*>(tex), tok_emb, pos_emb, segm_emb, tex_emb, x, t, c));
   return T2H_OK;
 }
 

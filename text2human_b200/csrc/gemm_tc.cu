@@ -148,6 +148,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ TapGemmDev P) {
   using C = Cfg<BN, MBLK>;
+  pdl_launch_dependents();  // the next kernel may start its prologue once every CTA of this one is running
   const int NA = P.a_slots, NB = P.b_slots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
@@ -201,6 +202,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // everything above touched only shared / tensor memory and kernel parameters; from here on the previous
+  // kernel's results are read (and buffers it may still be reading are overwritten)
+  pdl_wait();
 
   const int a_planes = (P.nterms == 3) ? 2 : 1;  // slabs per (group, chunk): hi [, lo]
   const int slab_bytes = P.slab_rows * P.TW * 128;
@@ -420,7 +424,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               (P.bias_mode == T2H_BIAS_ROW && row_ok) ? __ldg(P.bias + h * P.W + w) : 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * P.alpha + row_bias;
-          if (P.bias_mode == T2H_BIAS_COL) {
+          if (P.bias_mode == T2H_BIAS_COL && ch0 == 0) {  // split-K: the first k-slice carries the bias
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               if (col0 + i < P.n_out) {  // n_out % 4 == 0 in this mode
@@ -730,8 +734,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   if (Q.b_slots < 3) return fail(T2H_EINVAL, "tapgemm: shared-memory rings do not fit");
   int grid = P.total_work < num_sms() ? P.total_work : num_sms();
   // the full dynamic allocation also keeps it to one CTA (one TMEM allocation) per SM
-  tapgemm_kernel<BN, MBLK><<<grid, kThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
-  T2H_LAUNCH_OK();
+  T2H_CUDA(launch_pdl(tapgemm_kernel<BN, MBLK>, dim3(grid), dim3(kThreads), kDynSmem, stream, tmA, tmB, tmD, tmR, Q));
   return T2H_OK;
 }
 
@@ -758,8 +761,8 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  tapgemm_swap_kernel<MBLK><<<grid, kSwapThreads, kDynSmem, stream>>>(tmA, tmB, tmD, tmR, Q);
-  T2H_LAUNCH_OK();
+  T2H_CUDA(launch_pdl(tapgemm_swap_kernel<MBLK>, dim3(grid), dim3(kSwapThreads), kDynSmem, stream, tmA, tmB, tmD,
+                      tmR, Q));
   return T2H_OK;
 }
 
@@ -913,13 +916,13 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   // ---- split-K: k-slices of one tile go to different CTAs and are reduce-added into a zeroed output
   P.ksplit = 1;
   P.kper = P.kchunks;
-  if (p->k_split > 1 && !swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode == T2H_BIAS_NONE &&
+  if (p->k_split > 1 && !swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode != T2H_BIAS_ROW &&
       p->act == T2H_ACT_NONE && !p->gn_stats) {
     int ks = p->k_split < P.kchunks ? p->k_split : P.kchunks;
     P.kper = ceil_div(P.kchunks, ks);
     P.ksplit = ceil_div(P.kchunks, P.kper);
   } else {
-    T2H_CHECK_ARG(p->k_split <= 1, "tapgemm: k_split needs a plain aligned fp32 output (no bias/act/residual)");
+    T2H_CHECK_ARG(p->k_split <= 1, "tapgemm: k_split needs an aligned fp32 output and no row bias/act/residual");
   }
   T2H_CHECK_ARG((long long)P.total_tiles * P.ksplit < (1LL << 31), "tapgemm: too many work items");
   P.total_work = P.total_tiles * P.ksplit;

@@ -28,6 +28,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ TapGemmDev P) {
   using C = Cfg<128, MBLK>;
   constexpr int NPIX = MBLK * 128;  // pixels per tile = UMMA N
+  pdl_launch_dependents();  // the next kernel may start its prologue once every CTA of this one is running
   const int NA = P.a_slots, NB = P.b_slots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem =
@@ -79,6 +80,9 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  // everything above touched only shared / tensor memory and kernel parameters; from here on the previous
+  // kernel's results are read (and buffers it may still be reading are overwritten)
+  pdl_wait();
 
   const int a_planes = (P.nterms == 3) ? 2 : 1;
   const int slab_bytes = P.slab_rows * P.TW * 128;

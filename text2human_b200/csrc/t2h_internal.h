@@ -1,5 +1,6 @@
 // Shared host-side helpers for libt2h.so: error reporting and launch checks.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,34 @@ int num_sms();
 #define T2H_LAUNCH_OK() T2H_CUDA(cudaPeekAtLastError())
 
 static inline cudaStream_t as_stream(t2h_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// T2H_PDL=0 turns programmatic dependent launch off (A/B measurements)
+static inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("T2H_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// Launch a kernel that calls pdl_wait() before its first dependent global access, allowing it to overlap its
+// prologue with the previous kernel's tail (also inside CUDA-graph capture, where it becomes a programmatic edge).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -69,6 +69,13 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor is still running; `pdl_wait` blocks until every prerequisite grid has
+// completed and its memory is visible, `pdl_launch_dependents` lets the NEXT kernel's CTAs start their
+// prologue (barrier init, TMEM allocation, descriptor prefetch) early.  Both are no-ops without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // TMA store smem -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem, int c0, int c1, int c2,
                                              int c3) {

@@ -266,8 +266,25 @@ def conv3x3_s2(a_ph, w, bias, *, want_stats=False):
     return out
 
 
+# Split-K GEMMs reduce their k-slices with fp32 atomics (TMA reduce-add), so their results depend on the
+# arrival order at rounding level (~1e-7 relative).  Weight gradients use it by default (as cuDNN's wgrad
+# does); inference stays bit-reproducible run to run unless the caller opts in.
+SPLIT_K = {"wgrad": True, "inference": False}
+
+
+def set_split_k(wgrad=None, inference=None):
+    """enable / disable the (order-non-deterministic) split-K paths; returns the previous settings"""
+    old = dict(SPLIT_K)
+    if wgrad is not None:
+        SPLIT_K["wgrad"] = bool(wgrad)
+    if inference is not None:
+        SPLIT_K["inference"] = bool(inference)
+    return old
+
+
 def wgrad_k_split(M, Nout, K):
-    """k-slices per output tile so that a [M,Nout] weight gradient contracted over K tokens fills the GPU"""
+    """k-slices per output tile so that a GEMM with few [128 x 256] output tiles and a long contraction
+    (weight gradients; proj / fc2 at small batch) fills the GPU; 0 when splitting does not pay"""
     tiles = ((M + 127) // 128) * ((Nout + 255) // 256)
     ks = min((K + 63) // 64, 148 // max(tiles, 1))
     return ks if ks >= 2 else 0
@@ -276,8 +293,9 @@ def wgrad_k_split(M, Nout, K):
 def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None, k_split=0):
     """a: planes [T,M,K] (any leading dims are flattened by the caller);
     w: planes [T,1,Nout,K] (pack_linear_weight).  -> fp32 [M,Nout] or planes [T,M,Nout].
-    Serves 1x1 convs on NHWC activations and nn.Linear.  ``k_split`` >= 2 (weight gradients: small
-    output, long contraction) accumulates k-slices into a zeroed ``out``."""
+    Serves 1x1 convs on NHWC activations and nn.Linear.  ``k_split`` >= 2 (small output, long contraction)
+    ACCUMULATES into ``out``: out += alpha * a @ w^T (+ bias) -- a zeroed gradient buffer, or the residual stream."""
+    assert k_split < 2 or (out is not None and residual is None and not planes_out)
     _need_cuda(a, w)
     T, M, K = a.shape
     Nout = w.shape[2]

@@ -20,6 +20,17 @@ from . import ops
 from .vqgan_arch import _cached, _f32, _lin_w
 
 
+def _linear_residual(a, lin, x_res):
+    """x_res + lin(a).  With ``ops.set_split_k(inference=True)`` and few output tiles (small batch) the
+    contraction is split over the SMs and the k-slices are reduce-added into the residual stream in place
+    (faster, but the fp32 summation order then varies run to run); otherwise a fresh tensor is written."""
+    M, K = a.shape[1], a.shape[2]
+    ks = ops.wgrad_k_split(M, lin.out_features, K) if ops.SPLIT_K["inference"] else 0
+    if ks >= 2:
+        return ops.linear(a, _lin_w(lin), _f32(lin.bias), out=x_res, k_split=ks)
+    return ops.linear(a, _lin_w(lin), _f32(lin.bias), residual=x_res)
+
+
 class CausalSelfAttention(nn.Module):
     """multi-head self-attention (reference :9-71; runs non-causal)."""
 
@@ -49,7 +60,8 @@ class CausalSelfAttention(nn.Module):
 
     def attend(self, hn, x_res, B, T):
         """hn: LayerNorm'ed planes [Tt, B*T, C]; x_res: fp32 [B*T, C] residual stream.
-        Returns x_res + proj(attention(hn)) as fp32 [B*T, C]."""
+        Returns x_res + proj(attention(hn)) as fp32 [B*T, C]; at small batch the projection is split over
+        the contraction and accumulated INTO ``x_res`` (which is then the returned tensor)."""
         if self.causal:
             raise NotImplementedError("sampler='autoregressive' is never used by Text2Human")
         Tt, M, Cc = hn.shape
@@ -61,7 +73,7 @@ class CausalSelfAttention(nn.Module):
         s = ops.mha_scores(qk, B, T, nh)  # fp32 [B, nh, T, T]
         p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // nh))  # planes [Tt, B, nh, T, T]
         y = ops.mha_pv(p, vt, B, T, nh)  # planes [Tt, M, C]
-        return ops.linear(y, _lin_w(self.proj), _f32(self.proj.bias), residual=x_res)
+        return _linear_residual(y, self.proj, x_res)
 
     @torch.no_grad()
     def forward(self, x, layer_past=None):
@@ -97,13 +109,13 @@ class Block(nn.Module):
         x = self.attn.attend(h, x, B, T)
         h = ops.layer_norm(x, _f32(self.ln2.weight), _f32(self.ln2.bias), self.ln2.eps)
         m = ops.linear(h, _lin_w(self.mlp[0]), _f32(self.mlp[0].bias), planes_out=True, act=ops.ACT_GELU)
-        return ops.linear(m, _lin_w(self.mlp[2]), _f32(self.mlp[2].bias), residual=x)
+        return _linear_residual(m, self.mlp[2], x)
 
     @torch.no_grad()
     def forward(self, x, layer_past=None, return_present=False):
         assert layer_past is None
         B, T, Cc = x.shape
-        y = self.forward_rows(x.reshape(B * T, Cc).float().contiguous(), B, T).view(B, T, Cc)
+        y = self.forward_rows(x.reshape(B * T, Cc).float().clone(), B, T).view(B, T, Cc)  # updated in place
         if return_present:
             return y, None
         return y

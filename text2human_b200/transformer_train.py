@@ -292,8 +292,8 @@ class SamplerTrainer:
         """out[n_out, n_in] = dy^T x over all tokens; dy_t [T,n_out,M], x_t [T,n_in,M] (token-contiguous
         planes).  The output has few tiles and the contraction is long, so k-slices are spread over the SMs
         and reduce-added into the (zeroed) gradient buffer."""
-        ops.linear(dy_t, x_t.unsqueeze(1), out=out,
-                   k_split=ops.wgrad_k_split(dy_t.shape[1], x_t.shape[1], dy_t.shape[2]))
+        ks = ops.wgrad_k_split(dy_t.shape[1], x_t.shape[1], dy_t.shape[2]) if ops.SPLIT_K["wgrad"] else 0
+        ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)
 
     def _bucket_done(self, which, reduce):
         """gradients of a contiguous slice of the flat buffer are final: start their all-reduce (sum) now,

@@ -19,6 +19,8 @@ OPT = dict(codebook_size=18432, segm_codebook_size=1024, texture_codebook_size=1
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 ops.set_precision(prec)
+if os.environ.get("T2H_SPLITK_INFER"):
+    ops.set_split_k(inference=True)
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 s = Sampler(OPT).to(dev).eval()
