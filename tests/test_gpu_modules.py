@@ -246,7 +246,8 @@ def test_sampler_transformer_logits_and_sampling_loop(cuda, mode):
         got_sk = s.sampler_fn.forward_logits(idx, segm, tex)
     finally:
         ops.set_split_k(**old)
-    assert _rel(got_sk, want) < _tol(mode) and _rel(got_sk, got) < 1e-4
+    # (in fp16 mode an fp32-ulp change of the stream can flip an fp16 rounding downstream)
+    assert _rel(got_sk, want) < _tol(mode) and _rel(got_sk, got) < (1e-4 if mode == "fp32" else _tol(mode))
     if mode == "fp32":
         mask = R.blocky_mask(4, B, 512, 256, 64).to(cuda)
         gen = torch.Generator(device=cuda).manual_seed(2021)

@@ -386,7 +386,7 @@ class TransformerTextureAwareModel(nn.Module):
         """-> (continual tokens [B,T], own-codebook targets [B,T], texture ids [B,T]); the reference returns the
         targets as 18 lists with -1 fills (:154-170), of which each position uses exactly one"""
         B = image.shape[0]
-        z = conv1x1_nhwc(self.img_encoder.forward_nhwc(ops.nchw_to_nhwc(image)), self.img_quant_conv)
+        z = conv1x1_nhwc(self.img_encoder.forward_nhwc(image), self.img_quant_conv)   # NCHW in, NHWC out
         r = self.img_quantizer.forward_nhwc(z, texture_mask)
         return r["idx_cont"].view(B, -1), r["idx"].view(B, -1), r["ids"].view(B, -1).long()
 
