@@ -127,6 +127,12 @@ typedef struct t2h_tapgemm_params {
   double* gn_stats;      /* optional [n_img][32][2] (sum, sumsq) accumulators
                             of the fp32 output, for the following GroupNorm   */
   int32_t gn_cpg;        /* channels per group when gn_stats != NULL         */
+  int32_t a_mn;          /* 1: A is stored contraction-major -- element (row w, k) at a + k*a_sw + w (rows
+                            contiguous, a_sw = distance between consecutive k): A^T products without a
+                            transposed copy (weight gradients dY^T.X, P^T.dY).  Row GEMMs with one tap only */
+  int32_t b_mn;          /* 1: B is stored contraction-major -- element (n, k) at b + k*b_sn + n (output
+                            columns contiguous): X.W with W as stored [k][n] (dgrad with the forward's
+                            weight planes, att.V with V token-major)                                      */
   int64_t bias_sn;       /* BIAS_COL with n_img > 1: element distance between the bias vectors of consecutive
                             images (per-head biases of a batched GEMM); 0 = one shared vector          */
   int32_t k_split;       /* >= 2: D += alpha*A.B (+ column bias, once): the contraction of every output tile
@@ -260,8 +266,8 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
  *  loss.backward() + torch.optim.Adam.step()).  Dense gradients (dgrad / wgrad / attention) run on
  * t2h_tapgemm; these are the HBM-bound pieces around it.
  * ---------------------------------------------------------------------- */
-/* fp32 [g][r][c] -> fp16 planes of scale*x, transposed out_t[terms][g][c][r] (+ untransposed out_n, may be
- * NULL): wgrad contracts over rows, so both operands are needed row-contiguous.  `scale` (a power of two,
+/* fp32 [g][r][c] -> fp16 planes of scale*x, transposed out_t[terms][g][c][r] and / or untransposed out_n (either
+ * may be NULL, not both): wgrad contracts over rows, so both operands are needed row-contiguous.  `scale` (a power of two,
  * undone by the consuming GEMM's alpha) keeps small gradients out of fp16's subnormal range */
 int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms, float scale,
                         t2h_stream_t stream);

@@ -82,6 +82,55 @@ def test_split_k_weight_gradient_gemm(M, N, K):
         ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks, residual=base)
 
 
+@pytest.mark.parametrize("M,No,Ni", [(64, 64, 64), (1000, 512, 200), (8192, 1536, 512), (520, 96, 2048)])
+def test_mn_major_operands_wgrad_and_dgrad(M, No, Ni):
+    """tensor-core operands read contraction-major (no transposed copies): dW = dY^T X (both MN-major, plain
+    and split-K) and dX = dY W with the forward's [out,in] weight planes (B MN-major)"""
+    ops = _ops()
+    dy = torch.randn(M, No, device=DEV)
+    x = torch.randn(M, Ni, device=DEV)
+    w = torch.randn(No, Ni, device=DEV) / 8
+    dyp, xp = ops.f32_to_planes_rows(dy), ops.f32_to_planes_rows(x)
+    assert _rel(_join(dyp), dy) < 1e-6
+    want = dy.double().t() @ x.double()
+    out = torch.empty(No, Ni, device=DEV)
+    ops.wgrad(dyp, xp, out)
+    assert _rel(out, want) < 1e-4
+    ks = ops.wgrad_k_split(No, Ni, M)
+    if ks >= 2:
+        out2 = torch.zeros(No, Ni, device=DEV)
+        ops.wgrad(dyp, xp, out2, k_split=ks)
+        assert _rel(out2, want) < 1e-4
+    wp = ops.f32_to_planes_rows(w).unsqueeze(1)                      # [T,1,No,Ni] as the forward holds it
+    dx = ops.linear(dyp, wp, w_kn=True)                              # [M, Ni] = dY W
+    assert _rel(dx, dy.double() @ w.double()) < 1e-4
+    fwd = ops.linear(xp, wp)                                         # same planes, K-major: X W^T
+    assert _rel(fwd, x.double() @ w.double().t()) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,nh,hs", [(2, 32, 4, 16), (3, 160, 8, 16), (2, 512, 8, 64)])
+def test_attention_products_on_the_fused_qkv_layout(B, T, nh, hs):
+    """q|k|v side by side in one [M,3C] planes matrix: scores from column-sliced views, att.v with v
+    token-major (B MN-major), and the transposed-probability products of the backward pass (A MN-major)"""
+    ops = _ops()
+    C, M = nh * hs, B * T
+    qkv = torch.randn(M, 3 * C, device=DEV)
+    qkvp = ops.f32_to_planes_rows(qkv)
+    q, k, v = (qkv[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3).double() for i in range(3))
+    qp, kp, vp = qkvp[:, :, :C], qkvp[:, :, C:2 * C], qkvp[:, :, 2 * C:]
+    sc = ops.mha_scores(qp, B, T, nh, k=kp)
+    assert _rel(sc, q @ k.transpose(-1, -2)) < 1e-4
+    p = torch.softmax(torch.randn(B, nh, T, T, device=DEV), -1)
+    pp = ops.f32_to_planes_rows(p)
+    y = ops.mha_pv(pp, vp, B, T, nh, planes_out=False, v_tok=True)
+    want = (p.double() @ v).permute(0, 2, 1, 3).reshape(M, C)
+    assert _rel(y, want) < 1e-4
+    wide = torch.zeros(M, 3 * C, device=DEV)
+    ops.mha_pv(pp, vp, B, T, nh, planes_out=False, out=wide[:, C:2 * C], p_mn=True, v_tok=True, alpha=0.5)
+    want_t = 0.5 * (p.double().transpose(-1, -2) @ v).permute(0, 2, 1, 3).reshape(M, C)
+    assert _rel(wide[:, C:2 * C], want_t) < 1e-4 and float(wide[:, :C].abs().max()) == 0.0
+
+
 def test_colsum_gelu_layernorm_softmax_backward_kernels():
     ops = _ops()
     M, Cc = 200, 96

@@ -49,13 +49,13 @@ def test_trainer_flat_layout_aliases_parameters():
     tr.flat_p.add_(1.0)
     for k, v in net.state_dict().items():
         assert torch.equal(v, sd[k] + 1.0), k
-    # q|k weights and biases are adjacent so that one GEMM produces both gradients
+    # q|k|v weights and biases are adjacent so that one GEMM produces all three gradients
     a = net.blocks[0].attn
     C = cfg["bert_n_emb"]
-    wqk = tr._flat_view(tr.flat_p, a.query.weight, 2 * C, C)
-    assert torch.equal(wqk, torch.cat((a.query.weight, a.key.weight), 0))
-    bqk = tr._flat_view(tr.flat_p, a.query.bias, 1, 2 * C)[0]
-    assert torch.equal(bqk, torch.cat((a.query.bias, a.key.bias), 0))
+    wqkv = tr._flat_view(tr.flat_p, a.query.weight, 3 * C, C)
+    assert torch.equal(wqkv, torch.cat((a.query.weight, a.key.weight, a.value.weight), 0))
+    bqkv = tr._flat_view(tr.flat_p, a.query.bias, 1, 3 * C)[0]
+    assert torch.equal(bqkv, torch.cat((a.query.bias, a.key.bias, a.value.bias), 0))
     wh = tr._flat_view(tr.flat_p, net.head_list[0].weight, cfg["codebook_size"], C)
     assert torch.equal(wh, torch.cat([h.weight for h in net.head_list], 0))
     # gradient views alias the flat gradient buffer; buckets tile it without gaps

@@ -39,7 +39,7 @@ class TapGemmParams(C.Structure):
         ("bias", C.c_void_p), ("bias_mode", C.c_int32), ("act", C.c_int32),
         ("alpha", C.c_float),
         ("residual", C.c_void_p),
-        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
+        ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
     ]
 
 

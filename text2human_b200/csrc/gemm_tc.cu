@@ -33,6 +33,7 @@ struct TapGemmDev {
   int TW, TH;  // spatial box of one 128-row block
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int n_out, C, kchunks, nterms;
+  int a_mn, b_mn;  // operand stored contraction-major (rows / columns contiguous): MN-major UMMA descriptors
   int ksplit, kper, total_work;  // split-K: work item = (tile, k-slice); total_work = total_tiles * ksplit
   int a_term_imgs, a_bcast, b_term_g, b_batched, b_batched_h;
   // taps grouped by (dx, img_off): one activation slab per group
@@ -226,9 +227,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (P.debug & 4) {
                 mbar_arrive(&a_full[sa]);
               } else {
-                mbar_expect_tx(&a_full[sa], slab_bytes);
-                tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
-                            t.h0 + P.g_dy0[g], a_img + P.g_ioff[g] + pl * P.a_term_imgs);
+                if (P.a_mn) {
+                  // [k][row] storage: two boxes of 64 rows x 64 k per 128-row block
+                  mbar_expect_tx(&a_full[sa], kABlockBytes);
+#pragma unroll
+                  for (int hbox = 0; hbox < 2; ++hbox)
+                    tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot + hbox * 8192, t.w0 + 64 * hbox,
+                                ch * kBK, t.h0, a_img + pl * P.a_term_imgs);
+                } else {
+                  mbar_expect_tx(&a_full[sa], slab_bytes);
+                  tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
+                              t.h0 + P.g_dy0[g], a_img + P.g_ioff[g] + pl * P.a_term_imgs);
+                }
               }
               if (++sa == NA) {
                 sa = 0;
@@ -260,8 +270,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   mbar_arrive(&b_full[sb]);
                 } else {
                   mbar_expect_tx(&b_full[sb], C::kBSlot);
-                  tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
-                              b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                  if (P.b_mn) {
+                    // [k][column] storage: one box of 64 columns x 64 k per 64 output columns
+                    for (int q = 0; q < BN / 64; ++q)
+                      tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q, ch * kBK,
+                                  b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                  } else {
+                    tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
+                                b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                  }
                 }
                 if (++sb == NB) {
                   sb = 0;
@@ -278,11 +295,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // One thread; per MMA it only adds to the two descriptor low words (see umma_ksteps), which keeps
     // the issue stream well under the ~120 cycles an MMA occupies the tensor pipe.
     {  // the whole warp runs the loop; one elected lane issues the tcgen05 instructions
-      constexpr uint32_t IDESC = umma_idesc_f16(128, BN);
+      const uint32_t IDESC = umma_idesc_f16(128, BN) | (P.a_mn ? (1u << 15) : 0u) | (P.b_mn ? (1u << 16) : 0u);
+      const uint32_t a_step = P.a_mn ? kUmmaStepMN : kUmmaStepK, b_step = P.b_mn ? kUmmaStepMN : kUmmaStepK;
       const int last_steps = (P.C - (P.kchunks - 1) * kBK + 15) / 16;  // UMMA_K=16 steps
       const uint32_t row16 = (uint32_t)(P.TW * 128) >> 4;  // one slab image row, in 16-byte units
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_ring));
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(b_ring));
+      const uint32_t a_lo0 = P.a_mn ? umma_desc_lo_mn(smem_u32(a_ring)) : umma_desc_lo(smem_u32(a_ring));
+      const uint32_t b_lo0 = P.b_mn ? umma_desc_lo_mn(smem_u32(b_ring)) : umma_desc_lo(smem_u32(b_ring));
       constexpr uint32_t A16 = C::kASlot >> 4, B16 = C::kBSlot >> 4, BLK16 = kABlockBytes >> 4;
       const bool dbg_nomma = (P.debug & 2) != 0;
       const int ngroups = P.ngroups, kchunks = P.kchunks;
@@ -302,7 +320,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (dbg_nomma) return;
 #pragma unroll
           for (int mb = 0; mb < MBLK; ++mb)
-            { if (elect_one()) umma_ksteps(d_base + mb * BN, a_lo + mb * BLK16, b_lo, IDESC, ksteps, acc[mb]); acc[mb] = 1; __syncwarp(); }
+            { if (elect_one()) umma_ksteps(d_base + mb * BN, a_lo + mb * BLK16, b_lo, IDESC, ksteps, acc[mb], a_step, b_step); acc[mb] = 1; __syncwarp(); }
         };
         for (int g = 0; g < ngroups; ++g) {
           const int nt = P.g_ntaps[g];
@@ -797,6 +815,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   P.n_img = p->n_img; P.H = p->H; P.W = p->W;
   P.n_out = p->n_out; P.C = p->C; P.kchunks = (p->C + kBK - 1) / kBK; P.nterms = p->nterms;
   P.a_term_imgs = p->a_term_imgs; P.a_bcast = p->a_bcast;
+  P.a_mn = p->a_mn ? 1 : 0; P.b_mn = p->b_mn ? 1 : 0;
   P.b_term_g = p->b_term_g; P.b_batched = p->b_batched; P.b_batched_h = p->b_batched_h;
   P.d = p->d; P.d_mode = p->d_mode; P.d_terms = p->d_terms; P.d_plane = p->d_plane;
   P.d_sn = p->d_sn; P.d_sh = p->d_sh; P.d_sw = p->d_sw; P.d_sc = p->d_sc;
@@ -838,8 +857,14 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     }
     if (no_swap) swap = false;
   }
+  if (p->a_mn || p->b_mn) {
+    T2H_CHECK_ARG(rows_mode && p->ntaps == 1 && p->tap_dx[0] == 0 && p->tap_dy[0] == 0,
+                  "tapgemm: a_mn / b_mn operands need a row GEMM (H == 1 or tile_rows) with one tap");
+    swap = false;
+  }
   int BN = 16;
   while (BN < p->n_out && BN < 256) BN <<= 1;
+  if (p->b_mn && BN < 64) BN = 64;  // an MN-major B tile is made of whole 64-column boxes
   int MBLK = 1;
   if (swap) {
     BN = 128;
@@ -939,6 +964,10 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->a_W, (uint64_t)p->a_H, (uint64_t)p->a_imgs};
     uint64_t str[4] = {1, (uint64_t)p->a_sw, (uint64_t)p->a_sh, (uint64_t)p->a_sn};
     uint32_t box[4] = {(uint32_t)kBK, (uint32_t)TW, (uint32_t)P.slab_rows, 1};
+    if (p->a_mn) {  // (row, k, h, img): rows contiguous, a_sw = distance between consecutive k
+      dims[0] = (uint64_t)p->a_W; dims[1] = (uint64_t)p->C;
+      box[0] = 64; box[1] = (uint32_t)kBK; box[2] = 1;
+    }
     int rc = make_tmap(&tmA, p->a, 2, 4, dims, str, box, "tapgemm A");
     if (rc) return rc;
   }
@@ -948,6 +977,10 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     uint64_t str[4] = {1, (uint64_t)p->b_sn, (uint64_t)p->b_sg,
                        (uint64_t)(g2 > 1 ? p->b_sg2 : p->b_sg)};
     uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
+    if (p->b_mn) {  // (n, k, g, g2): output columns contiguous, b_sn = distance between consecutive k
+      dims[0] = (uint64_t)p->n_out; dims[1] = (uint64_t)p->C;
+      box[0] = 64; box[1] = (uint32_t)kBK;
+    }
     int rc = make_tmap(&tmB, p->b, 2, 4, dims, str, box, "tapgemm B");
     if (rc) return rc;
   }

@@ -204,18 +204,29 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
 __device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) {
   return (static_cast<uint64_t>(kUmmaDescHiK128) << 32) | lo;
 }
+// MN-major ("transposed") operand, as TMA deposits [64 k rows][64 MN elements] boxes with the 128-byte
+// swizzle, one 8 KB box per 64 rows/columns of the operand: same high word (SBO = 1024 B between groups of
+// 8 k rows), LBO = 8192 B (box to box along MN) in the low word, and a K=16 step advances the start address
+// by 16 k rows = 2048 B.  The instruction descriptor carries the major-ness (bit 15 for A, 16 for B).
+// Encoding verified on hardware by tools/umma_mn_probe.cu (profiles/r01_umma_mn_major_probe.log).
+constexpr uint32_t kUmmaStepK = 2;     // descriptor low-word advance per K=16 step, K-major
+constexpr uint32_t kUmmaStepMN = 128;  // ... MN-major (2048 B >> 4)
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | ((8192u >> 4) << 16);
+}
 // `ksteps` (<= 4) K=16 steps of D (+)= A*B; acc is 0 only for the very first MMA of an accumulator.
 __device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
-                                            int ksteps, uint32_t& acc) {
+                                            int ksteps, uint32_t& acc, uint32_t a_step = kUmmaStepK,
+                                            uint32_t b_step = kUmmaStepK) {
   if (ksteps == 4) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      umma_f16(d_tmem, umma_desc_join(a_lo + 2 * j), umma_desc_join(b_lo + 2 * j), idesc, acc);
+      umma_f16(d_tmem, umma_desc_join(a_lo + a_step * j), umma_desc_join(b_lo + b_step * j), idesc, acc);
       acc = 1;
     }
   } else {
     for (int j = 0; j < ksteps; ++j) {
-      umma_f16(d_tmem, umma_desc_join(a_lo + 2 * j), umma_desc_join(b_lo + 2 * j), idesc, acc);
+      umma_f16(d_tmem, umma_desc_join(a_lo + a_step * j), umma_desc_join(b_lo + b_step * j), idesc, acc);
       acc = 1;
     }
   }

@@ -54,6 +54,7 @@ __global__ void f32_to_planes_t_kernel(const float* __restrict__ x, __half* __re
       }
     }
   }
+  if (!out_t) return;  // plain conversion only (uniform across the grid)
   __syncthreads();
   for (int i = ty; i < 64; i += 8) {
     const int c = c0 + i, r = r0 + 2 * tx;
@@ -378,7 +379,7 @@ extern "C" {
 
 int t2h_f32_to_planes_t(const float* x, void* out_t, void* out_n, int g, int r, int c, int terms, float scale,
                         t2h_stream_t stream) {
-  T2H_CHECK_ARG(x && out_t && g > 0 && r > 0 && c > 0, "f32_to_planes_t: bad args");
+  T2H_CHECK_ARG(x && (out_t || out_n) && g > 0 && r > 0 && c > 0, "f32_to_planes_t: bad args");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "f32_to_planes_t: terms=%d", terms);
   dim3 grid(ceil_div(r, 64), ceil_div(c, 64), g), block(32, 8);
   f32_to_planes_t_kernel<<<grid, block, 0, as_stream(stream)>>>(

@@ -90,7 +90,7 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
-             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0):
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -120,6 +120,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.gn_cpg = gn_cpg if gn_stats is not None else 0
     p.k_split = k_split
     p.bias_sn = bias_sn
+    p.a_mn, p.b_mn = a_mn, b_mn
     _count()
     if _PROFILE["on"]:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -290,7 +291,8 @@ def wgrad_k_split(M, Nout, K):
     return ks if ks >= 2 else 0
 
 
-def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None, k_split=0):
+def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, alpha=1.0, out=None, k_split=0,
+           w_kn=False):
     """a: planes [T,M,K] (any leading dims are flattened by the caller);
     w: planes [T,1,Nout,K] (pack_linear_weight).  -> fp32 [M,Nout] or planes [T,M,Nout].
     Serves 1x1 convs on NHWC activations and nn.Linear.  ``k_split`` >= 2 (small output, long contraction)
@@ -298,8 +300,14 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
     assert k_split < 2 or (out is not None and residual is None and not planes_out)
     _need_cuda(a, w)
     T, M, K = a.shape
-    Nout = w.shape[2]
-    assert w.shape[3] == K and a.stride(2) == 1, (a.shape, w.shape)
+    if w_kn:
+        # w: planes [T,1,K,Nout] -- the contraction index is the ROW of the stored matrix (e.g. the forward
+        # weight [out,in] used for the data gradient dX = dY.W): consumed as an MN-major operand, no transpose
+        Nout = w.shape[3]
+        assert w.shape[2] == K and a.stride(2) == 1 and w.stride(3) == 1, (a.shape, w.shape)
+    else:
+        Nout = w.shape[2]
+        assert w.shape[3] == K and a.stride(2) == 1, (a.shape, w.shape)
     if out is None:
         out = _alloc_out((M, Nout), planes_out, T, a.device)
     a_sw = a.stride(1)
@@ -309,7 +317,25 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
              b_sg=w.stride(0),
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32,
              d_strides=(0, 0, out.stride(-2), 1), d_plane=out.stride(0) if planes_out else 0,
-             bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual, k_split=k_split)
+             bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual, k_split=k_split,
+             b_mn=1 if w_kn else 0)
+    return out
+
+
+def wgrad(dy, x, out, k_split=0, alpha=1.0):
+    """out[n_out, n_in] += alpha * dy^T @ x over the rows (tokens).  dy planes [T,M,n_out], x planes [T,M,n_in]
+    exactly as the forward / backward passes hold them (row = token): both are consumed as MN-major operands,
+    so no transposed copy exists.  With ``k_split`` >= 2 the token range is split over the SMs and reduce-added
+    into ``out`` (which the caller zeroed); with 0 ``out`` is overwritten."""
+    _need_cuda(dy, x, out)
+    T, M, No = dy.shape
+    Ni = x.shape[2]
+    assert x.shape[:2] == dy.shape[:2] and dy.stride(2) == 1 and x.stride(2) == 1 and out.shape == (No, Ni)
+    _tapgemm(a=dy, a_term_imgs=1, a_imgs=T, a_bcast=0, n_img=1, H=1, W=No, a_H=1, a_W=No, Cc=M,
+             a_sw=dy.stride(1), a_sh=dy.stride(0), a_sn=dy.stride(0),
+             b=x, b_term_g=1, b_groups=T, b_batched=0, n_out=Ni, b_sn=x.stride(1), b_sg=x.stride(0),
+             taps=_TAPS_1, d=out, d_mode=OUT_F32, d_strides=(0, 0, out.stride(0), 1), alpha=alpha,
+             k_split=k_split, a_mn=1, b_mn=1)
     return out
 
 
@@ -338,46 +364,60 @@ def bmm_nt(a, b, *, planes_out=False, alpha=1.0, bias_row=None, a_bcast=False, b
     return out
 
 
-def mha_scores(qk, B, Tn, nh, alpha=1.0):
+def mha_scores(q, B, Tn, nh, alpha=1.0, k=None):
     """Multi-head q @ k^T without head transposes (transformer_arch.py:41-58).
-    qk: planes [T, B*Tn, 2C] holding q in columns [0,C) and k in [C,2C), heads side by side.
-    -> fp32 [B, nh, Tn, Tn].  (h, img) of the tap-GEMM act as (batch, head)."""
-    _need_cuda(qk)
-    T, M, C2 = qk.shape
-    Cc = C2 // 2
+    q, k: planes [T, B*Tn, C] with the heads side by side -- possibly column-sliced views of a wider matrix
+    (e.g. of the fused q|k|v projection); with ``k=None``, ``q`` is [T, B*Tn, 2C] holding q in columns [0,C)
+    and k in [C,2C).  -> fp32 [B, nh, Tn, Tn].  (h, img) of the tap-GEMM act as (batch, head)."""
+    if k is None:
+        Cc = q.shape[2] // 2
+        q, k = q[:, :, :Cc], q[:, :, Cc:]
+    _need_cuda(q, k)
+    T, M, Cc = q.shape
     hs = Cc // nh
-    assert M == B * Tn and qk.is_contiguous()
-    out = torch.empty((B, nh, Tn, Tn), dtype=torch.float32, device=qk.device)
-    plane = qk.stride(0)
-    assert plane % hs == 0
-    kview = qk[:, :, Cc:]
-    _tapgemm(a=qk, a_term_imgs=plane // hs, a_imgs=(T - 1) * (plane // hs) + nh, a_bcast=0,
-             n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=hs, a_sw=C2, a_sh=Tn * C2, a_sn=hs, tile_rows=1,
-             b=kview, b_term_g=B, b_groups=T * B, b_sg=Tn * C2, b_batched_h=1,
-             b_groups2=nh, b_sg2=hs, b_batched=1, n_out=Tn, b_sn=C2,
+    assert M == B * Tn and k.shape == q.shape and q.stride(2) == 1 and k.stride(2) == 1
+    ldq, ldk = q.stride(1), k.stride(1)
+    out = torch.empty((B, nh, Tn, Tn), dtype=torch.float32, device=q.device)
+    plane = q.stride(0)
+    assert plane % hs == 0 and (T == 1 or k.stride(0) == M * ldk)
+    _tapgemm(a=q, a_term_imgs=plane // hs, a_imgs=(T - 1) * (plane // hs) + nh, a_bcast=0,
+             n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=hs, a_sw=ldq, a_sh=Tn * ldq, a_sn=hs, tile_rows=1,
+             b=k, b_term_g=B, b_groups=T * B, b_sg=Tn * ldk, b_batched_h=1,
+             b_groups2=nh, b_sg2=hs, b_batched=1, n_out=Tn, b_sn=ldk,
              taps=_TAPS_1, d=out, d_mode=OUT_F32, d_strides=(Tn * Tn, nh * Tn * Tn, Tn, 1), alpha=alpha)
     return out
 
 
-def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True, alpha=1.0):
+def mha_pv(p, vt, B, Tn, nh, out=None, planes_out=True, alpha=1.0, p_mn=False, v_tok=False):
     """Multi-head att @ v (transformer_arch.py:65-67).  p: planes [T,B,nh,Tn,Tn];
-    vt: planes [T,B,C,Tn] (v transposed: channels x tokens).  -> planes [T, B*Tn, C] (or fp32 [B*Tn, C])
-    with the heads re-assembled side by side.  ``out`` may be a column-sliced view of a wider matrix."""
+    vt: planes [T,B,C,Tn] (v transposed: channels x tokens), or with ``v_tok`` planes [T,B*Tn,C] token-major
+    (possibly a column-sliced view of the fused q|k|v projection; consumed MN-major).  ``p_mn`` uses p^T
+    (out[j] = sum_i p[i,j] v[i], the value / key gradients) without a transposed copy.
+    -> planes [T, B*Tn, C] (or fp32 [B*Tn, C]) with the heads re-assembled side by side.  ``out`` may be a
+    column-sliced view of a wider matrix."""
     _need_cuda(p, vt)
     T = p.shape[0]
-    Cc = vt.shape[2]
+    assert p.is_contiguous()
+    if v_tok:
+        Cc = vt.shape[2]
+        ldv = vt.stride(1)
+        assert vt.shape[1] == B * Tn and vt.stride(2) == 1 and (T == 1 or vt.stride(0) == B * Tn * ldv)
+        b_kw = dict(b_sg=Tn * ldv, b_sg2=Cc // nh, b_sn=ldv, b_mn=1)
+    else:
+        Cc = vt.shape[2]
+        assert vt.is_contiguous()
+        b_kw = dict(b_sg=Cc * Tn, b_sg2=(Cc // nh) * Tn, b_sn=Tn, b_mn=0)
     hs = Cc // nh
-    assert p.is_contiguous() and vt.is_contiguous()
     if out is None:
         out = _alloc_out((B * Tn, Cc), planes_out, T, p.device)
     ld = out.stride(-2)
     _tapgemm(a=p, a_term_imgs=B * nh, a_imgs=T * B * nh, a_bcast=0,
              n_img=nh, H=B, W=Tn, a_H=B, a_W=Tn, Cc=Tn, a_sw=Tn, a_sh=nh * Tn * Tn, a_sn=Tn * Tn,
              tile_rows=1,
-             b=vt, b_term_g=B, b_groups=T * B, b_sg=Cc * Tn, b_batched_h=1,
-             b_groups2=nh, b_sg2=hs * Tn, b_batched=1, n_out=hs, b_sn=Tn,
+             b=vt, b_term_g=B, b_groups=T * B, b_batched_h=1,
+             b_groups2=nh, b_batched=1, n_out=hs,
              taps=_TAPS_1, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=(hs, Tn * ld, ld, 1),
-             d_plane=out.stride(0) if planes_out else 0, alpha=alpha)
+             d_plane=out.stride(0) if planes_out else 0, alpha=alpha, a_mn=1 if p_mn else 0, **b_kw)
     return out
 
 
@@ -597,6 +637,19 @@ def vq_gather(codebook, idx, book_id, *, B, Hz, Wz, Cz, ps=1, want_nchw=True, wa
 # ----------------------------------------------------------------------------
 # training (backward / optimiser) kernels
 # ----------------------------------------------------------------------------
+def f32_to_planes_rows(x, terms=None, scale=1.0):
+    """fp32 [..., C] -> planes [T, ..., C] of scale*x (no layout change)"""
+    _need_cuda(x)
+    terms = terms or get_terms()
+    assert x.is_contiguous() and x.dtype == torch.float32
+    Cc = x.shape[-1]
+    R = x.numel() // Cc
+    out = torch.empty((terms,) + tuple(x.shape), dtype=torch.float16, device=x.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_f32_to_planes_t(_ptr(x), None, _ptr(out), 1, R, Cc, terms, scale, _stream()))
+    return out
+
+
 def f32_to_planes_t(x, terms=None, want_plain=True, scale=1.0):
     """fp32 [G,R,C] (or [R,C]) -> (planes [T,G,R,C] or None, transposed planes [T,G,C,R]) of scale*x"""
     _need_cuda(x)

@@ -3,8 +3,8 @@
 Same class names, constructor/forward signatures and ``state_dict`` keys as the
 reference.  torch ``nn.Linear`` / ``nn.LayerNorm`` /
 ``nn.Embedding`` objects are parameter containers only; the arithmetic runs in
-libt2h: embedding-sum, LayerNorm, tcgen05 GEMMs (fused q|k projection, v^T
-projection, per-head q k^T and att v without head transposes, MLP with fused
+libt2h: embedding-sum, LayerNorm, tcgen05 GEMMs (fused q|k|v projection, per-head
+q k^T and att v without head or v transposes, MLP with fused
 GELU, one N=18*1024 GEMM for the 18 heads), row softmax.
 
 The sampler is always non-causal on the Text2Human path (sampler='absorbing',
@@ -50,29 +50,29 @@ class CausalSelfAttention(nn.Module):
             mask = torch.tril(torch.ones(block_size, block_size))
             self.register_buffer("mask", mask.view(1, 1, block_size, block_size))
 
-    def _qk_packed(self):
+    def _qkv_packed(self):
+        """q | k | v projections as ONE [3C, C] weight (and bias): one GEMM instead of three"""
         t = ops.get_terms()
-        w = _cached(self, ("wqk", t), (self.query.weight, self.key.weight),
-                    lambda: ops.pack_linear_weight(torch.cat((self.query.weight, self.key.weight), 0), t))
-        b = _cached(self, ("bqk",), (self.query.bias, self.key.bias),
-                    lambda: torch.cat((self.query.bias, self.key.bias), 0).float().contiguous())
+        ws = (self.query.weight, self.key.weight, self.value.weight)
+        bs = (self.query.bias, self.key.bias, self.value.bias)
+        w = _cached(self, ("wqkv", t), ws, lambda: ops.pack_linear_weight(torch.cat(ws, 0), t))
+        b = _cached(self, ("bqkv",), bs, lambda: torch.cat(bs, 0).float().contiguous())
         return w, b
 
     def attend(self, hn, x_res, B, T):
         """hn: LayerNorm'ed planes [Tt, B*T, C]; x_res: fp32 [B*T, C] residual stream.
-        Returns x_res + proj(attention(hn)) as fp32 [B*T, C]; at small batch the projection is split over
-        the contraction and accumulated INTO ``x_res`` (which is then the returned tensor)."""
+        Returns x_res + proj(attention(hn)) as fp32 [B*T, C]; at small batch, with
+        ``ops.set_split_k(inference=True)``, the projection is accumulated INTO ``x_res``."""
         if self.causal:
             raise NotImplementedError("sampler='autoregressive' is never used by Text2Human")
         Tt, M, Cc = hn.shape
         nh = self.n_head
-        wqk, bqk = self._qk_packed()
-        qk = ops.linear(hn, wqk, bqk, planes_out=True)  # [Tt, M, 2C]  (q | k)
-        vt = ops.bmm_nt(_lin_w(self.value), hn.view(Tt, B, T, Cc), planes_out=True,
-                        bias_row=_f32(self.value.bias), a_bcast=True)  # [Tt, B, C, T]
-        s = ops.mha_scores(qk, B, T, nh)  # fp32 [B, nh, T, T]
+        wqkv, bqkv = self._qkv_packed()
+        qkv = ops.linear(hn, wqkv, bqkv, planes_out=True)  # [Tt, M, 3C]  (q | k | v), heads side by side
+        s = ops.mha_scores(qkv[:, :, :Cc], B, T, nh, k=qkv[:, :, Cc:2 * Cc])  # fp32 [B, nh, T, T]
         p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // nh))  # planes [Tt, B, nh, T, T]
-        y = ops.mha_pv(p, vt, B, T, nh)  # planes [Tt, M, C]
+        # v stays token-major inside qkv: the tensor core reads it as an MN-major operand (no v^T copy)
+        y = ops.mha_pv(p, qkv[:, :, 2 * Cc:], B, T, nh, v_tok=True)  # planes [Tt, M, C]
         return _linear_residual(y, self.proj, x_res)
 
     @torch.no_grad()

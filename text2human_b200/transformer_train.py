@@ -52,8 +52,8 @@ class SamplerTrainer:
         order = [("emb", [m.tok_emb.weight, m.pos_emb, m.segm_emb.weight, m.texture_emb.weight, m.start_tok])]
         for i, blk in enumerate(m.blocks):
             a = blk.attn
-            order.append((f"block{i}", [blk.ln1.weight, blk.ln1.bias, a.query.weight, a.key.weight, a.query.bias,
-                                        a.key.bias, a.value.weight, a.value.bias, a.proj.weight, a.proj.bias,
+            order.append((f"block{i}", [blk.ln1.weight, blk.ln1.bias, a.query.weight, a.key.weight, a.value.weight,
+                                        a.query.bias, a.key.bias, a.value.bias, a.proj.weight, a.proj.bias,
                                         blk.ln2.weight, blk.ln2.bias, blk.mlp[0].weight, blk.mlp[0].bias,
                                         blk.mlp[2].weight, blk.mlp[2].bias]))
         order.append(("head", [m.ln_f.weight, m.ln_f.bias] + [h.weight for h in m.head_list]))
@@ -89,23 +89,20 @@ class SamplerTrainer:
         return flat[off:off + rows * cols].view(rows, cols)
 
     def _weight_planes(self):
-        """fp16 planes of every GEMM weight for this step, as (W [T,1,N,K], W^T [T,1,K,N]) pairs made by
-        one conversion launch each (forward uses W, the data-gradient GEMMs use W^T)"""
+        """fp16 planes [T,1,out,in] of every GEMM weight for this step (one conversion launch each).  The forward
+        uses them K-major (y = x W^T); the data-gradient GEMMs read the SAME planes MN-major (dX = dY W)."""
         m = self.m
         C, F4 = m.n_embd, 4 * m.n_embd
 
-        def pair(p, rows, cols):
-            n, t = ops.f32_to_planes_t(self._flat_view(self.flat_p, p, rows, cols))
-            return n.unsqueeze(1), t.unsqueeze(1)
+        def planes(p, rows, cols):
+            return ops.f32_to_planes_rows(self._flat_view(self.flat_p, p, rows, cols)).unsqueeze(1)
 
         wp = []
         for blk in m.blocks:
             a = blk.attn
-            wp.append(dict(qk=pair(a.query.weight, 2 * C, C), v=pair(a.value.weight, C, C),
-                           proj=pair(a.proj.weight, C, C), fc1=pair(blk.mlp[0].weight, F4, C),
-                           fc2=pair(blk.mlp[2].weight, C, F4)))
-        heads = pair(m.head_list[0].weight, m.num_head * m.head_class_num, C)
-        return wp, heads
+            wp.append(dict(qkv=planes(a.query.weight, 3 * C, C), proj=planes(a.proj.weight, C, C),
+                           fc1=planes(blk.mlp[0].weight, F4, C), fc2=planes(blk.mlp[2].weight, C, F4)))
+        return wp, planes(m.head_list[0].weight, m.num_head * m.head_class_num, C)
 
     def _drop_packed_caches(self):
         # the inference mirrors cache packed weights keyed on torch's version counters, which the raw-pointer
@@ -127,31 +124,27 @@ class SamplerTrainer:
         B, T = idx.shape
         C = m.n_embd
         nh = m.blocks[0].attn.n_head
-        Tt = ops.get_terms()
         x = ops.embed_sum(idx, segm, tex, m.tok_emb.weight.detach(), m.pos_emb.detach()[0],
                           m.segm_emb.weight.detach(), m.texture_emb.weight.detach())
         saved = []
-        for blk in m.blocks:
+        for blk, w in zip(m.blocks, wp):
             a = blk.attn
             s = {"x_in": x}
             h1 = ops.layer_norm(x, blk.ln1.weight.detach(), blk.ln1.bias.detach(), blk.ln1.eps)
-            w = wp[len(saved)]
-            bqk = self._flat_view(self.flat_p, a.query.bias, 1, 2 * C)[0]
-            qk = ops.linear(h1, w["qk"][0], bqk, planes_out=True)
-            vt = ops.bmm_nt(w["v"][0], h1.view(Tt, B, T, C), planes_out=True,
-                            bias_row=a.value.bias.detach(), a_bcast=True)
-            sc = ops.mha_scores(qk, B, T, nh)
+            bqkv = self._flat_view(self.flat_p, a.query.bias, 1, 3 * C)[0]
+            qkv = ops.linear(h1, w["qkv"], bqkv, planes_out=True)                      # [Tt, M, 3C]: q | k | v
+            sc = ops.mha_scores(qkv[:, :, :C], B, T, nh, k=qkv[:, :, C:2 * C])
             p = ops.softmax_rows(sc, scale=1.0 / math.sqrt(C // nh))
-            y = ops.mha_pv(p, vt, B, T, nh)
-            x_mid = ops.linear(y, w["proj"][0], a.proj.bias.detach(), residual=x)
+            y = ops.mha_pv(p, qkv[:, :, 2 * C:], B, T, nh, v_tok=True)
+            x_mid = ops.linear(y, w["proj"], a.proj.bias.detach(), residual=x)
             h2 = ops.layer_norm(x_mid, blk.ln2.weight.detach(), blk.ln2.bias.detach(), blk.ln2.eps)
-            pre = ops.linear(h2, w["fc1"][0], blk.mlp[0].bias.detach())
+            pre = ops.linear(h2, w["fc1"], blk.mlp[0].bias.detach())
             g = ops.gelu_fwd(pre)
-            x = ops.linear(g, w["fc2"][0], blk.mlp[2].bias.detach(), residual=x_mid)
-            s.update(h1=h1, qk=qk, vt=vt, p=p, y=y, x_mid=x_mid, h2=h2, pre=pre, g=g)
+            x = ops.linear(g, w["fc2"], blk.mlp[2].bias.detach(), residual=x_mid)
+            s.update(h1=h1, qkv=qkv, p=p, y=y, x_mid=x_mid, h2=h2, pre=pre, g=g)
             saved.append(s)
         hf = ops.layer_norm(x, m.ln_f.weight.detach(), m.ln_f.bias.detach(), m.ln_f.eps)
-        logits = ops.linear(hf, w_heads[0])
+        logits = ops.linear(hf, w_heads)
         return logits.view(B * T, m.num_head, m.head_class_num), saved, x, hf
 
     # ------------------------------------------------------------------ loss + backward
@@ -165,9 +158,7 @@ class SamplerTrainer:
         C = m.n_embd
         M = B * T
         nh = m.blocks[0].attn.n_head
-        hs = C // nh
-        Tt = ops.get_terms()
-        scale = 1.0 / math.sqrt(hs)
+        scale = 1.0 / math.sqrt(C // nh)
         self.flat_g.zero_()
         self._handles = []
         # Static loss scale (a power of two, undone inside the Adam kernel): the gradient operands of the
@@ -202,12 +193,10 @@ class SamplerTrainer:
 
         # ---- heads + final LayerNorm
         NK = m.num_head * m.head_class_num
-        dl_n, dl_t = ops.f32_to_planes_t(dlogits)                       # [Tt,M,NK], [Tt,NK,M]
-        hf_t = ops.planes_transpose(hf.unsqueeze(1))[:, 0]              # [Tt,C,M]
-        g_heads = self._flat_view(self.flat_g, m.head_list[0].weight, NK, C)
-        self._wgrad(dl_t, hf_t, g_heads)                # dW_heads = dlogits^T hf
-        d_hf = ops.linear(dl_n, w_heads[1])                             # [M, C]
-        del dlogits, dl_n, dl_t
+        dl = ops.f32_to_planes_rows(dlogits)                              # [Tt, M, NK]
+        self._wgrad(dl, hf, self._flat_view(self.flat_g, m.head_list[0].weight, NK, C))   # dW_heads = dlogits^T hf
+        d_hf = ops.linear(dl, w_heads, w_kn=True)                        # [M, C] = dlogits W_heads
+        del dlogits, dl
         dx = torch.zeros((M, C), dtype=torch.float32, device=x_0.device)  # running gradient of the stream
         ops.layernorm_bwd_(dx, d_hf, x_last, m.ln_f.weight.detach(), self.g(m.ln_f.weight), self.g(m.ln_f.bias),
                            m.ln_f.eps, accumulate=False)
@@ -218,56 +207,40 @@ class SamplerTrainer:
             blk, s, w = m.blocks[li], saved[li], wp[li]
             a = blk.attn
             fc1, fc2 = blk.mlp[0], blk.mlp[2]
+            q, k, v = s["qkv"][:, :, :C], s["qkv"][:, :, C:2 * C], s["qkv"][:, :, 2 * C:]
             # MLP: x_out = x_mid + fc2(gelu(fc1(ln2(x_mid))))
-            dxo_n, dxo_t = ops.f32_to_planes_t(dx)
+            dxo = ops.f32_to_planes_rows(dx)
             ops.colsum_(self.g(fc2.bias), dx)
-            g_t = ops.planes_transpose(s["g"].unsqueeze(1))[:, 0]                       # [Tt,F,M]
-            self._wgrad(dxo_t, g_t, self.g(fc2.weight))                   # dW2 [C,F]
-            d_g = ops.linear(dxo_n, w["fc2"][1])                                            # [M,F]
+            self._wgrad(dxo, s["g"], self.g(fc2.weight))                              # dW2 [C,F] = dxo^T g
+            d_g = ops.linear(dxo, w["fc2"], w_kn=True)                                # [M,F]  = dxo W2
             d_a = ops.gelu_bwd(s["pre"], d_g)
-            da_n, da_t = ops.f32_to_planes_t(d_a)
+            da = ops.f32_to_planes_rows(d_a)
             ops.colsum_(self.g(fc1.bias), d_a)
-            h2_t = ops.planes_transpose(s["h2"].unsqueeze(1))[:, 0]                      # [Tt,C,M]
-            self._wgrad(da_t, h2_t, self.g(fc1.weight))                   # dW1 [F,C]
-            d_h2 = ops.linear(da_n, w["fc1"][1])                                            # [M,C]
+            self._wgrad(da, s["h2"], self.g(fc1.weight))                              # dW1 [F,C]
+            d_h2 = ops.linear(da, w["fc1"], w_kn=True)                                # [M,C]
             ops.layernorm_bwd_(dx, d_h2, s["x_mid"], blk.ln2.weight.detach(), self.g(blk.ln2.weight),
-                               self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True)       # dx = d x_mid
+                               self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True)   # dx = d x_mid
             # attention output projection: x_mid = x_in + proj(y)
-            dxm_n, dxm_t = ops.f32_to_planes_t(dx)
+            dxm = ops.f32_to_planes_rows(dx)
             ops.colsum_(self.g(a.proj.bias), dx)
-            y_t = ops.planes_transpose(s["y"].unsqueeze(1))[:, 0]
-            self._wgrad(dxm_t, y_t, self.g(a.proj.weight))                # dWp [C,C]
-            dyv = torch.empty((Tt, M, 2 * C), dtype=torch.float16, device=dx.device)      # [d_y | v]
-            ops.linear(dxm_n, w["proj"][1], planes_out=True, out=dyv[:, :, :C])            # d_y
-            ops.planes_transpose(s["vt"], out=dyv.view(Tt, B, T, 2 * C)[..., C:])         # v token-major
-            # attention core
-            dy_t = ops.planes_transpose(dyv.view(Tt, B, T, 2 * C)[..., :C])               # [Tt,B,C,T]
-            p_t = ops.planes_transpose(s["p"].view(Tt, B * nh, T, T)).view(Tt, B, nh, T, T)
-            dv = ops.mha_pv(p_t, dy_t, B, T, nh, planes_out=False)                        # fp32 [M,C]
-            dp = ops.mha_scores(dyv, B, T, nh)                                            # [B,nh,T,T]
+            self._wgrad(dxm, s["y"], self.g(a.proj.weight))                           # dWp [C,C]
+            d_y = ops.linear(dxm, w["proj"], w_kn=True, planes_out=True)              # planes [Tt,M,C]
+            # attention core; the three gradients land side by side in d_qkv [M, 3C]
+            d_qkv = torch.empty((M, 3 * C), dtype=torch.float32, device=dx.device)
+            ops.mha_pv(s["p"], d_y, B, T, nh, planes_out=False, out=d_qkv[:, 2 * C:], p_mn=True, v_tok=True)  # dV
+            dp = ops.mha_scores(d_y, B, T, nh, k=v)                                   # dP = dY V^T
             ds = ops.softmax_bwd(s["p"], dp, scale)
-            ds_n, ds_t = ops.f32_to_planes_t(ds.view(B * nh, T, T), scale=DS)
-            qk4 = s["qk"].view(Tt, B, T, 2 * C)
-            k_t = ops.planes_transpose(qk4[..., C:])                                      # [Tt,B,C,T]
-            q_t = ops.planes_transpose(qk4[..., :C])
-            d_qk = torch.empty((M, 2 * C), dtype=torch.float32, device=dx.device)
-            ops.mha_pv(ds_n.view(Tt, B, nh, T, T), k_t, B, T, nh, planes_out=False, out=d_qk[:, :C],
-                       alpha=1.0 / DS)                                                    # dQ
-            ops.mha_pv(ds_t.view(Tt, B, nh, T, T), q_t, B, T, nh, planes_out=False, out=d_qk[:, C:],
-                       alpha=1.0 / DS)                                                    # dK
-            # q|k projection
-            dqk_n, dqk_t = ops.f32_to_planes_t(d_qk)
-            ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 2 * C)[0], d_qk)     # [q.bias | k.bias]
-            h1_t = ops.planes_transpose(s["h1"].unsqueeze(1))[:, 0]                       # [Tt,C,M]
-            self._wgrad(dqk_t, h1_t, self._flat_view(self.flat_g, a.query.weight, 2 * C, C))
-            d_h1 = ops.linear(dqk_n, w["qk"][1])                                          # [M,C]
-            # v projection
-            dv_n, dv_t = ops.f32_to_planes_t(dv)
-            ops.colsum_(self.g(a.value.bias), dv)
-            self._wgrad(dv_t, h1_t, self.g(a.value.weight))               # dWv [C,C]
-            d_h1 = ops.linear(dv_n, w["v"][1], residual=d_h1)
+            dsp = ops.f32_to_planes_rows(ds, scale=DS).view(-1, B, nh, T, T)
+            ops.mha_pv(dsp, k, B, T, nh, planes_out=False, out=d_qkv[:, :C], alpha=1.0 / DS, v_tok=True)     # dQ
+            ops.mha_pv(dsp, q, B, T, nh, planes_out=False, out=d_qkv[:, C:2 * C], alpha=1.0 / DS, p_mn=True,
+                       v_tok=True)                                                    # dK = dS^T Q
+            # fused q|k|v projection
+            dqkv = ops.f32_to_planes_rows(d_qkv)
+            ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 3 * C)[0], d_qkv)
+            self._wgrad(dqkv, s["h1"], self._flat_view(self.flat_g, a.query.weight, 3 * C, C))
+            d_h1 = ops.linear(dqkv, w["qkv"], w_kn=True)                              # [M,C]
             ops.layernorm_bwd_(dx, d_h1, s["x_in"], blk.ln1.weight.detach(), self.g(blk.ln1.weight),
-                               self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True)       # dx = d x_in
+                               self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True)   # dx = d x_in
             saved[li] = None
             if li % self.bucket_layers == 0:
                 hi = min(self.n_layers, li + self.bucket_layers)
@@ -288,12 +261,12 @@ class SamplerTrainer:
         self._handles = []
 
     @staticmethod
-    def _wgrad(dy_t, x_t, out):
-        """out[n_out, n_in] = dy^T x over all tokens; dy_t [T,n_out,M], x_t [T,n_in,M] (token-contiguous
-        planes).  The output has few tiles and the contraction is long, so k-slices are spread over the SMs
+    def _wgrad(dy, x, out):
+        """out[n_out, n_in] = dy^T x over all tokens; dy [T,M,n_out], x [T,M,n_in] token-major planes, read
+        MN-major.  The output has few tiles and the contraction is long, so k-slices are spread over the SMs
         and reduce-added into the (zeroed) gradient buffer."""
-        ks = ops.wgrad_k_split(dy_t.shape[1], x_t.shape[1], dy_t.shape[2]) if ops.SPLIT_K["wgrad"] else 0
-        ops.linear(dy_t, x_t.unsqueeze(1), out=out, k_split=ks)
+        ks = ops.wgrad_k_split(dy.shape[2], x.shape[2], dy.shape[1]) if ops.SPLIT_K["wgrad"] else 0
+        ops.wgrad(dy, x, out, k_split=ks)
 
     def _bucket_done(self, which, reduce):
         """gradients of a contiguous slice of the flat buffer are final: start their all-reduce (sum) now,
