@@ -5,8 +5,9 @@ Mirrors ``TransformerTextureAwareModel._train_loss`` / ``q_sample`` / ``optimize
 (models/transformer_model.py:212-303: absorbing-diffusion masking, 18 masked cross-entropies,
 re-weighted ELBO, ``loss.backward()``, ``torch.optim.Adam.step()``) for the ``TransformerMultiHead``
 mirror.  Forward and backward contractions (dgrad, wgrad, attention gradients) all run on
-``t2h_tapgemm``; operands that a gradient GEMM contracts over rows are transposed by
-``t2h_planes_transpose`` / ``t2h_f32_to_planes_t``.  Parameters, gradients and Adam moments live in flat
+``t2h_tapgemm``; a gradient GEMM that contracts over the rows of a stored matrix (dY^T X, P^T dY, dY W) reads it
+as an MN-major tensor-core operand (``a_mn`` / ``b_mn``), so no transposed copy of any activation, gradient or
+weight is made.  Parameters, gradients and Adam moments live in flat
 fp32 buffers (the ``nn.Parameter``s are views), so the optimiser is one kernel launch and the gradient
 all-reduce works on contiguous buckets that are launched as soon as the backward pass has finished the
 layers they cover (overlap with the remaining backward).
