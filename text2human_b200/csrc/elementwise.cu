@@ -581,9 +581,9 @@ int t2h_softmax_rows(const float* s, void* out, int64_t rows, int cols, float sc
   const long long plane = rows * cols;
   cudaStream_t st = as_stream(stream);
   if (cols <= 512)
-    T2H_CUDA(launch_pdl(softmax_rows_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, s, o, rows, cols, scale, terms, plane));
+    T2H_CUDA(launch_pdl(softmax_rows_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, s, o, rows, cols, scale, terms, plane));
   else
-    T2H_CUDA(launch_pdl(softmax_rows_kernel<64>, dim3(grid), dim3(warps * 32), 0, st, s, o, rows, cols, scale, terms, plane));
+    T2H_CUDA(launch_pdl(softmax_rows_kernel<64>, dim3(grid), dim3(warps * 32), 0, st, 1, s, o, rows, cols, scale, terms, plane));
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -599,9 +599,9 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
   const long long plane = rows * c;
   cudaStream_t st = as_stream(stream);
   if (c <= 512)
-    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, o, rows, c, eps, terms, plane));
+    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane));
   else
-    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, x, gamma, beta, o, rows, c, eps, terms, plane));
+    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane));
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -611,7 +611,7 @@ int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex, c
                   int t, int c, t2h_stream_t stream) {
   T2H_CHECK_ARG(idx && segm && tex && tok_emb && pos_emb && segm_emb && tex_emb && x, "embed_sum: null");
   T2H_CHECK_ARG(b > 0 && t > 0 && c > 0 && c % 4 == 0, "embed_sum: bad shape");
-  T2H_CUDA(launch_pdl(embed_sum_kernel, dim3(b * t), dim3(128), 0, as_stream(stream),
+  T2H_CUDA(launch_pdl(embed_sum_kernel, dim3(b * t), dim3(128), 0, as_stream(stream), 1,
                       reinterpret_cast<const long long*>(idx), reinterpret_cast<const long long*>(segm),
                       reinterpret_cast<const long long*>(tex), tok_emb, pos_emb, segm_emb, tex_emb, x, t, c));
   return T2H_OK;

@@ -33,6 +33,8 @@ struct TapGemmDev {
   int TW, TH;  // spatial box of one 128-row block
   int tiles_w, tiles_h, n_tiles_n, total_tiles;
   int n_out, C, kchunks, nterms;
+  int pair;        // 1: launched as clusters of two CTAs that own vertically adjacent row tiles and share every
+                   // weight tile: each CTA loads every other B tile and TMA-multicasts it to both
   int a_mn, b_mn;  // operand stored contraction-major (rows / columns contiguous): MN-major UMMA descriptors
   int ksplit, kper, total_work;  // split-K: work item = (tile, k-slice); total_work = total_tiles * ksplit
   int a_term_imgs, a_bcast, b_term_g, b_batched, b_batched_h;
@@ -88,6 +90,18 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmDev& P, int tile, 
   TileCoord t;
   int n_tile = tile % P.n_tiles_n;
   int m_tile = tile / P.n_tiles_n;
+  if (P.pair) {
+    // `tile` enumerates (row-tile pair, column tile); this CTA takes row 2*pair + rank.  An odd row count
+    // leaves the last pair's second CTA with an out-of-range row tile (zero-filled loads, clipped stores).
+    m_tile = 2 * m_tile + (int)(blockIdx.x & 1);
+    if (m_tile >= P.n_img * P.tiles_h * P.tiles_w) {  // rows beyond the matrix: every access is out of range
+      t.img = 0;
+      t.h0 = 0;
+      t.w0 = P.tiles_w * P.TW;
+      t.n0 = n_tile * bn;
+      return t;
+    }
+  }
   int per_img = P.tiles_h * P.tiles_w;
   t.img = m_tile / per_img;
   int rem = m_tile - t.img * per_img;
@@ -185,7 +199,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], P.pair ? 2 : 1);  // pair: both CTAs' MMA warps release a (multicast) weight slot
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -203,18 +217,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (P.pair) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   // everything above touched only shared / tensor memory and kernel parameters; from here on the previous
   // kernel's results are read (and buffers it may still be reading are overwritten)
   pdl_wait();
 
   const int a_planes = (P.nterms == 3) ? 2 : 1;  // slabs per (group, chunk): hi [, lo]
   const int slab_bytes = P.slab_rows * P.TW * 128;
+  // pair mode: the two CTAs of a cluster walk the same sequence of (row-tile pair, column tile) work items
+  const int work0 = P.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_stride = P.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t pair_rank = P.pair ? (blockIdx.x & 1u) : 0u;
 
   if (warp == 0) {
     // ---------------------------------------------- A producer (activation slabs)
     if (lane == 0) {
       int sa = 0, pa = 0;
-      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+      for (int work = work0; work < P.total_work; work += work_stride) {
         const int tile = work % P.total_tiles;
         const int ch0 = (work / P.total_tiles) * P.kper;
         const int ch1 = min(P.kchunks, ch0 + P.kper);
@@ -253,8 +272,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------- B producer (weight tiles)
     if (lane == 0) {
       int sb = 0, pb = 0;
+      uint32_t bj = 0;  // running index of weight-tile loads (pair mode: even ones are rank 0's, odd ones rank 1's)
       const int b_planes = a_planes;
-      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+      for (int work = work0; work < P.total_work; work += work_stride) {
         const int tile = work % P.total_tiles;
         const int ch0 = (work / P.total_tiles) * P.kper;
         const int ch1 = min(P.kchunks, ch0 + P.kper);
@@ -270,7 +290,19 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   mbar_arrive(&b_full[sb]);
                 } else {
                   mbar_expect_tx(&b_full[sb], C::kBSlot);
-                  if (P.b_mn) {
+                  if (P.pair) {
+                    // weight tiles alternate between the two CTAs; the issuer multicasts to both
+                    if ((bj++ & 1u) == pair_rank) {
+                      if (P.b_mn) {
+                        for (int q = 0; q < BN / 64; ++q)
+                          tma_load_4d_mc(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q,
+                                         ch * kBK, b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2, 3);
+                      } else {
+                        tma_load_4d_mc(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
+                                       b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2, 3);
+                      }
+                    }
+                  } else if (P.b_mn) {
                     // [k][column] storage: one box of 64 columns x 64 k per 64 output columns
                     for (int q = 0; q < BN / 64; ++q)
                       tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q, ch * kBK,
@@ -305,7 +337,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool dbg_nomma = (P.debug & 2) != 0;
       const int ngroups = P.ngroups, kchunks = P.kchunks;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
-      for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+      for (int work = work0; work < P.total_work; work += work_stride) {
         const int tile = work % P.total_tiles;
         const int ch0 = (work / P.total_tiles) * P.kper;
         const int ch1 = min(P.kchunks, ch0 + P.kper);
@@ -345,13 +377,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&b_full[sb], pb);
                 tc_fence_after();
                 batch(ahi + dy, b_lo0 + sb * B16, ksteps);
-                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                { if (elect_one()) { if (P.pair) umma_commit_mc(&b_empty[sb], 3); else umma_commit(&b_empty[sb]); } __syncwarp(); }
                 if (++sb == NB) { sb = 0; pb ^= 1; }
               } else {
                 mbar_wait(&b_full[sb], pb);  // B lo
                 tc_fence_after();
                 batch(ahi + dy, b_lo0 + sb * B16, ksteps);  // hi*lo
-                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                { if (elect_one()) { if (P.pair) umma_commit_mc(&b_empty[sb], 3); else umma_commit(&b_empty[sb]); } __syncwarp(); }
                 if (++sb == NB) { sb = 0; pb ^= 1; }
                 mbar_wait(&b_full[sb], pb);  // B hi
                 tc_fence_after();
@@ -363,7 +395,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   tc_fence_after();
                 }
                 batch(alo + dy, bhi, ksteps);  // lo*hi
-                { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
+                { if (elect_one()) { if (P.pair) umma_commit_mc(&b_empty[sb], 3); else umma_commit(&b_empty[sb]); } __syncwarp(); }
                 if (++sb == NB) { sb = 0; pb ^= 1; }
               }
             }
@@ -388,7 +420,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t res_par[2] = {0, 0};
     int tile_par = 0;  // gsum buffer of this tile
 
-    for (int work = blockIdx.x; work < P.total_work; work += gridDim.x) {
+    for (int work = work0; work < P.total_work; work += work_stride) {
         const int tile = work % P.total_tiles;
         const int ch0 = (work / P.total_tiles) * P.kper;
         const int ch1 = min(P.kchunks, ch0 + P.kper);
@@ -662,6 +694,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (P.pair) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
@@ -751,8 +784,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   if (Q.b_slots < 3) return fail(T2H_EINVAL, "tapgemm: shared-memory rings do not fit");
   int grid = P.total_work < num_sms() ? P.total_work : num_sms();
+  if (P.pair) {
+    grid = 2 * P.total_work;
+    if (grid > (num_sms() & ~1)) grid = num_sms() & ~1;
+  }
   // the full dynamic allocation also keeps it to one CTA (one TMEM allocation) per SM
-  T2H_CUDA(launch_pdl(tapgemm_kernel<BN, MBLK>, dim3(grid), dim3(kThreads), kDynSmem, stream, tmA, tmB, tmD, tmR, Q));
+  T2H_CUDA(launch_pdl(tapgemm_kernel<BN, MBLK>, dim3(grid), dim3(kThreads), kDynSmem, stream, P.pair ? 2 : 1, tmA,
+                      tmB, tmD, tmR, Q));
   return T2H_OK;
 }
 
@@ -779,8 +817,8 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  T2H_CUDA(launch_pdl(tapgemm_swap_kernel<MBLK>, dim3(grid), dim3(kSwapThreads), kDynSmem, stream, tmA, tmB, tmD,
-                      tmR, Q));
+  T2H_CUDA(launch_pdl(tapgemm_swap_kernel<MBLK>, dim3(grid), dim3(kSwapThreads), kDynSmem, stream, 1, tmA, tmB,
+                      tmD, tmR, Q));
   return T2H_OK;
 }
 
@@ -951,6 +989,22 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   }
   T2H_CHECK_ARG((long long)P.total_tiles * P.ksplit < (1LL << 31), "tapgemm: too many work items");
   P.total_work = P.total_tiles * P.ksplit;
+  // ---- CTA pairs: plain row GEMMs with at least two row tiles run as clusters of two CTAs on vertically
+  // adjacent row tiles that share each weight tile through TMA multicast (-1/3 of the L2->SM operand bytes)
+  P.pair = 0;
+  {
+    static int pair_on = -1;
+    if (pair_on < 0) {
+      const char* e = getenv("T2H_PAIR");
+      pair_on = e ? atoi(e) : 0;
+    }
+    if (pair_on && !swap && rows_mode && !p->tile_rows && p->n_img == 1 && p->H == 1 && P.ksplit == 1 &&
+        !p->a_bcast && !p->b_batched && !p->b_batched_h && P.tiles_w >= 2 && P.total_tiles >= 32) {
+      P.pair = 1;
+      P.total_tiles = ceil_div(P.tiles_w, 2) * P.n_tiles_n;
+      P.total_work = P.total_tiles;
+    }
+  }
   if (p->gn_stats && !swap) {
     T2H_CHECK_ARG(P.epi_mode == EPI_TMA_F32, "tapgemm: gn_stats needs an aligned fp32 NHWC output");
     T2H_CHECK_ARG(p->gn_cpg >= 2 && (p->gn_cpg & (p->gn_cpg - 1)) == 0 && p->n_out % p->gn_cpg == 0,
