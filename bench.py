@@ -180,6 +180,38 @@ def side_workloads(dev, precision):
                                       tokens_per_s_256_steps=2048 / (ms * 256 / 1e3), extrapolated=True,
                                       algorithmic_tflops=4 * 99.86 / ms, precision=precision,
                                       launch="CUDA graph replay of the transformer forward per step")
+        # the refine half of sample_and_refine: sampled top tokens -> top codebook gather -> UNet/FCN
+        # index prediction -> bottom gather -> DecoderRes -> Decoder, batched (the reference decodes one by one)
+        del sm
+        torch.cuda.empty_cache()
+        from text2human_b200.pipeline import SampleFromParsingModel
+        opt = dict(HIER_OPT)
+        opt.update(SAMPLER_OPT)
+        opt.update(bot_codebook_spatial_size=2, index_pred_encoder_in_channels=256, index_pred_fc_in_channels=64,
+                   index_pred_fc_in_index=4, index_pred_fc_channels=64, index_pred_fc_num_convs=1,
+                   index_pred_fc_concat_input=False, index_pred_fc_dropout_ratio=0.1,
+                   index_pred_fc_num_classes=512, index_pred_fc_align_corners=False, segm_double_z=False,
+                   segm_z_channels=32, segm_resolution=512, segm_in_channels=24, segm_out_ch=24, segm_ch=64,
+                   segm_ch_mult=[1, 1, 2, 2, 4], segm_num_res_blocks=1, segm_attn_resolutions=[16],
+                   segm_dropout=0.0, segm_num_segm_classes=24, segm_n_embed=1024, segm_embed_dim=32)
+        torch.manual_seed(6)
+        with contextlib.redirect_stdout(sys.stderr):
+            sp = SampleFromParsingModel(opt).to(dev).eval()
+        tex = torch.nn.functional.interpolate(tm, (32, 16), mode="nearest")[:, 0].long()
+        top = torch.randint(0, 1024, (4, 32, 16), device=dev)
+        top_list = [torch.where(tex == k, top, torch.full_like(top, -1)) for k in range(18)]
+        for _ in range(2):
+            sp.decode_top_tokens(top_list, tm)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            sp.decode_top_tokens(top_list, tm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out["config4_refine_decode"] = dict(batch=4, ms_per_batch=ms, img_per_s=4 / (ms / 1e3), precision=precision,
+                                            stages="top gather, 1x1, UNet+FCN index prediction, bottom gather, "
+                                                   "DecoderRes, Decoder(bot_h), clamp")
     except Exception as exc:  # side measurements must never break the headline line
         out["error"] = repr(exc)
     return out

@@ -143,14 +143,8 @@ def test_real_size_index_prediction_matches_restatement(cuda):
     assert n_checked > 0.9 * int((torch.stack(want_list) >= 0).sum())
 
 
-def test_sample_and_refine_decode_matches_restatement(cuda):
-    """sampled top tokens -> image in [0,1] through the whole refine chain (sample_model.py:215-246), with the
-    reference's configs/sample_from_parsing.yml sizes, batched"""
-    _ops()
-    from oracle import indexpred_ref as IR
-    from oracle import vqgan_ref
-    from text2human_b200.pipeline import SampleFromParsingModel
-    from bench import SAMPLER_OPT, HIER_OPT
+def _sample_opt():
+    from bench import HIER_OPT, SAMPLER_OPT
     opt = dict(HIER_OPT)
     opt.update(SAMPLER_OPT)
     opt.update(bot_codebook_spatial_size=2, index_pred_encoder_in_channels=256, index_pred_fc_in_channels=64,
@@ -160,6 +154,43 @@ def test_sample_and_refine_decode_matches_restatement(cuda):
                segm_in_channels=24, segm_out_ch=24, segm_ch=64, segm_ch_mult=[1, 1, 2, 2, 4], segm_num_res_blocks=1,
                segm_attn_resolutions=[16], segm_dropout=0.0, segm_num_segm_classes=24, segm_n_embed=1024,
                segm_embed_dim=32)
+    return opt
+
+
+def test_sample_and_refine_end_to_end_plumbing(cuda):
+    """parsing map + texture mask -> images through every stage of SampleFromParsingModel (segm tokenizer,
+    4 diffusion steps of the sampler, both codebook gathers, UNet/FCN index prediction, DecoderRes, Decoder);
+    the stages' numerics are covered individually, this checks they compose: shapes, ranges, determinism under
+    a seeded generator, and that a different seed changes the result"""
+    _ops()
+    from text2human_b200.pipeline import SampleFromParsingModel
+    torch.manual_seed(41)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SampleFromParsingModel(_sample_opt())
+    for sub, seed in ((m.index_pred_guidance_encoder, 43), (m.index_pred_decoder, 44)):
+        sub.load_state_dict(R.fill_state_dict(R.spec_of(sub), seed), strict=True)
+    m = m.to(cuda).eval()
+    B = 2
+    segm = R.blocky_mask(45, B, 512, 256, 16, n_ids=24).to(cuda)
+    mask = R.blocky_mask(46, B, 512, 256, 64).to(cuda)
+    imgs = []
+    for seed in (7, 7, 8):
+        g = torch.Generator(device=cuda).manual_seed(seed)
+        imgs.append(m.sample_and_refine(segm, mask, sample_steps=4, generator=g))
+    img = imgs[0]
+    assert img.shape == (B, 3, 512, 256) and img.dtype == torch.float32
+    assert bool(torch.isfinite(img).all()) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+    assert torch.equal(imgs[0], imgs[1]) and not torch.equal(imgs[0], imgs[2])
+
+
+def test_sample_and_refine_decode_matches_restatement(cuda):
+    """sampled top tokens -> image in [0,1] through the whole refine chain (sample_model.py:215-246), with the
+    reference's configs/sample_from_parsing.yml sizes, batched"""
+    _ops()
+    from oracle import indexpred_ref as IR
+    from oracle import vqgan_ref
+    from text2human_b200.pipeline import SampleFromParsingModel
+    opt = _sample_opt()
     torch.manual_seed(31)
     with contextlib.redirect_stdout(io.StringIO()):
         m = SampleFromParsingModel(opt)
