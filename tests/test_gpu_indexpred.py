@@ -160,8 +160,9 @@ def _sample_opt():
 def test_sample_and_refine_end_to_end_plumbing(cuda):
     """parsing map + texture mask -> images through every stage of SampleFromParsingModel (segm tokenizer,
     4 diffusion steps of the sampler, both codebook gathers, UNet/FCN index prediction, DecoderRes, Decoder);
-    the stages' numerics are covered individually, this checks they compose: shapes, ranges, determinism under
-    a seeded generator, and that a different seed changes the result"""
+    the stages' numerics are covered individually, this checks they compose: shapes, ranges, reproducibility
+    under a seeded generator (to rounding: the fused GroupNorm statistics are accumulated with atomics, so the
+    conv stacks are order-dependent in the last fp32 bits), and that a different seed changes the result"""
     _ops()
     from text2human_b200.pipeline import SampleFromParsingModel
     torch.manual_seed(41)
@@ -180,7 +181,8 @@ def test_sample_and_refine_end_to_end_plumbing(cuda):
     img = imgs[0]
     assert img.shape == (B, 3, 512, 256) and img.dtype == torch.float32
     assert bool(torch.isfinite(img).all()) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
-    assert torch.equal(imgs[0], imgs[1]) and not torch.equal(imgs[0], imgs[2])
+    assert float((imgs[0] - imgs[1]).abs().max()) < 1e-4
+    assert float((imgs[0] - imgs[2]).abs().max()) > 1e-2
 
 
 def test_sample_and_refine_decode_matches_restatement(cuda):
