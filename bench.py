@@ -141,6 +141,7 @@ def side_workloads(dev, precision):
     """BASELINE configs 3 and 4, a few iterations each (reported next to the headline, not instead of it)."""
     import contextlib
     import golden_recipes as R
+    from text2human_b200 import ops
     from text2human_b200.pipeline import HierarchyVQSpatialTextureAwareModel, Sampler
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -180,6 +181,23 @@ def side_workloads(dev, precision):
                                       tokens_per_s_256_steps=2048 / (ms * 256 / 1e3), extrapolated=True,
                                       algorithmic_tflops=4 * 99.86 / ms, precision=precision,
                                       launch="CUDA graph replay of the transformer forward per step")
+        # opt-in small-batch mode: proj / fc2 split over the contraction and reduce-added into the residual
+        # stream (fp32 summation order then varies run to run, so it is not the default)
+        old_sk = ops.set_split_k(inference=True)
+        try:
+            sm._graphs.clear()
+            sm.sample_fn(segm, tm, sample_steps=4, generator=gen)
+            torch.cuda.synchronize()
+            e0.record()
+            sm.sample_fn(segm, tm, sample_steps=steps, generator=gen)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_sk = e0.elapsed_time(e1) / steps
+            out["config4_sampler"]["split_k_opt_in"] = dict(ms_per_diffusion_step=ms_sk,
+                                                            tokens_per_s_256_steps=2048 / (ms_sk * 256 / 1e3))
+        finally:
+            ops.set_split_k(**old_sk)
+            sm._graphs.clear()
         # the refine half of sample_and_refine: sampled top tokens -> top codebook gather -> UNet/FCN
         # index prediction -> bottom gather -> DecoderRes -> Decoder, batched (the reference decodes one by one)
         del sm

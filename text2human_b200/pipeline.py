@@ -238,7 +238,7 @@ class Sampler(nn.Module):
         m = self.sampler_fn
         if not use_graph:
             return m.forward_logits
-        key = (B, T, str(device), ops.get_terms())
+        key = (B, T, str(device), ops.get_terms(), ops.SPLIT_K["inference"])
         g = self._graphs.get(key)
         if g is None:
             ex = (torch.full((B, T), self.mask_id, dtype=torch.long, device=device),
