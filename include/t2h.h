@@ -157,6 +157,10 @@ int t2h_nchw_to_planes(const float* x, void* out, int n, int c, int h, int w,
 /* fp32 NHWC [N,H,W,C] -> fp32 NCHW.  Exit of the modules. */
 int t2h_nhwc_to_nchw(const float* x, float* out, int n, int c, int h, int w,
                      t2h_stream_t stream);
+/* Image write-out (sample_model.py:244-253 + torchvision.utils.save_image): fp32 NCHW x -> uint8 NHWC
+ * out = uint8(clamp(clamp(x*scale + shift, 0, 1) * 255 + 0.5, 0, 255)); c <= 4 */
+int t2h_pack_u8(const float* x, uint8_t* out, int n, int c, int h, int w, float scale, float shift,
+                t2h_stream_t stream);
 /* fp32 NCHW -> fp32 NHWC */
 int t2h_nchw_to_nhwc(const float* x, float* out, int n, int c, int h, int w,
                      t2h_stream_t stream);

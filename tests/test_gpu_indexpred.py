@@ -143,6 +143,24 @@ def test_real_size_index_prediction_matches_restatement(cuda):
     assert n_checked > 0.9 * int((torch.stack(want_list) >= 0).sum())
 
 
+def test_image_packing_and_write_out(cuda, tmp_path):
+    """save_image's quantisation (torchvision: mul(255).add_(0.5).clamp_(0,255).to(uint8)) on the GPU, bit-exact,
+    incl. the fused (x+1)/2 map and clamp; files round-trip through PIL"""
+    ops = _ops()
+    from PIL import Image
+    from text2human_b200.pipeline import save_images
+    x = torch.rand(2, 3, 37, 21, device=cuda) * 1.2 - 0.1            # some values outside [0,1]
+    want = x.clamp(0, 1).mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    assert torch.equal(ops.pack_u8(x), want)
+    y = x * 2 - 1
+    want2 = ((y + 1) / 2).clamp(0, 1).mul(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    got2 = ops.pack_u8(y, scale=0.5, shift=0.5)
+    assert int((got2.int() - want2.int()).abs().max()) <= 1          # the fused affine map rounds once, torch twice
+    save_images(x, str(tmp_path), ["a.png", "b.png"])
+    back = np.asarray(Image.open(tmp_path / "b.png"))
+    assert np.array_equal(back, want[1].cpu().numpy())
+
+
 def _sample_opt():
     from bench import HIER_OPT, SAMPLER_OPT
     opt = dict(HIER_OPT)

@@ -68,6 +68,25 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restri
   }
 }
 
+// Image write-out packing (save_image in sample_and_refine, sample_model.py:249-253; torchvision:
+// mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(uint8)): x fp32 NCHW -> uint8 NHWC, the layout PNG
+// encoders take.  `scale`/`shift` let the decoder's [-1,1] output be mapped here ((x+1)/2 -> scale .5, shift .5)
+// instead of in a separate pass.  One thread per pixel; C <= 4.
+__global__ void pack_u8_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, int C, int HW,
+                               long long total, float scale, float shift) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW;
+    const int p = (int)(i - n * HW);
+    for (int c = 0; c < C; ++c) {
+      float v = x[(n * C + c) * HW + p] * scale + shift;
+      v = fminf(fmaxf(v, 0.f), 1.f);                       // dec.clamp_(0, 1)
+      v = fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f);  // save_image's quantisation (two roundings, no FMA)
+      out[i * C + c] = (unsigned char)v;                   // truncation, as .to(torch.uint8)
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // fp32 NHWC -> fp16 planes, with optional nearest x2 / space-to-depth
 // one thread = 8 channels of one output position (32 B in, 16 B out per plane)
@@ -644,6 +663,15 @@ int t2h_argmax_heads(const float* logits, const int64_t* head, int64_t* out, int
   const int warps = 8;
   argmax_heads_kernel<<<(unsigned)ceil_div64(rows, warps), warps * 32, 0, as_stream(stream)>>>(
       logits, reinterpret_cast<const long long*>(head), reinterpret_cast<long long*>(out), rows, n_heads, ncls);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_pack_u8(const float* x, uint8_t* out, int n, int c, int h, int w, float scale, float shift,
+                t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && out && n > 0 && c > 0 && c <= 4 && h > 0 && w > 0, "pack_u8: bad args");
+  const long long total = (long long)n * h * w;
+  pack_u8_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, out, c, h * w, total, scale, shift);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -768,3 +768,15 @@ def argmax_heads(logits, head):
     _count(1)
     _lib.check(_lib.load().t2h_argmax_heads(_ptr(logits), _ptr(head.contiguous()), _ptr(out), M, G, ncls, _stream()))
     return out
+
+
+def pack_u8(x, scale=1.0, shift=0.0):
+    """fp32 NCHW image batch -> uint8 NHWC as torchvision's save_image quantises it (after an optional affine
+    map and the clamp to [0,1])"""
+    _need_cuda(x)
+    x = _f32c(x)
+    N, Cc, H, W = x.shape
+    out = torch.empty((N, H, W, Cc), dtype=torch.uint8, device=x.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_pack_u8(_ptr(x), _ptr(out), N, Cc, H, W, scale, shift, _stream()))
+    return out

@@ -342,14 +342,31 @@ class SampleFromParsingModel(nn.Module):
         return dec.add_(1.0).mul_(0.5).clamp_(0, 1)
 
     @torch.no_grad()
-    def sample_and_refine(self, segm, texture_mask, temp=1.0, sample_steps=None, generator=None):
-        """segm [B,1,H,W] parsing ids, texture_mask [B,1,H,W] texture ids -> images [B,3,512,256] in [0,1]"""
+    def sample_and_refine(self, segm, texture_mask, temp=1.0, sample_steps=None, generator=None, save_dir=None,
+                          img_name=None):
+        """segm [B,1,H,W] parsing ids, texture_mask [B,1,H,W] texture ids -> images [B,3,512,256] in [0,1].
+        With ``save_dir`` and ``img_name`` (a list of B file names) the images are also written as the
+        reference does (sample_model.py:249-253: one file per sample, save_image quantisation)."""
         B = segm.shape[0]
         segm_tokens = self.segm.get_quantized_segm(segm).view(B, -1)
         top_list, _ = self.sampler.sample_fn(segm_tokens, texture_mask, temp=temp, sample_steps=sample_steps,
                                              generator=generator)
         h, w = self.shape
-        return self.decode_top_tokens([t.view(B, h, w) for t in top_list], texture_mask)
+        dec = self.decode_top_tokens([t.view(B, h, w) for t in top_list], texture_mask)
+        if save_dir is not None and img_name is not None:
+            save_images(dec, save_dir, img_name)
+        return dec
+
+
+def save_images(images, save_dir, names):
+    """images fp32 NCHW in [0,1] -> one image file per sample (what torchvision's save_image writes for a
+    single image: uint8(x*255+0.5)); the packing runs on the GPU, the encoder (PIL) on the host"""
+    import os
+    from PIL import Image
+    u8 = ops.pack_u8(images).cpu().numpy()                      # [B,H,W,C]
+    os.makedirs(save_dir, exist_ok=True)
+    for arr, name in zip(u8, names):
+        Image.fromarray(arr if arr.shape[-1] != 1 else arr[..., 0]).save(os.path.join(save_dir, name))
 
 
 class TransformerTextureAwareModel(nn.Module):
