@@ -263,6 +263,10 @@ int t2h_embed_sum(const int64_t* idx, const int64_t* segm, const int64_t* tex,
 /* LayerNorm over the last dim (eps 1e-5) of fp32 [rows, c] -> fp16 planes (:80-81,:231) */
 int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* out,
                   int64_t rows, int c, float eps, int terms, t2h_stream_t stream);
+/* the same, row r written to row row_map[r] of a planes buffer of out_rows rows (the sampler's final LayerNorm
+ * groups the positions by texture so that each position only meets its own head, transformer_arch.py:268-273) */
+int t2h_layernorm_scatter(const float* x, const float* gamma, const float* beta, void* out, int64_t rows, int c,
+                          float eps, int terms, const int64_t* row_map, int64_t out_rows, t2h_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Training step of the index-prediction transformer

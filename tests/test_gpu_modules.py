@@ -248,6 +248,17 @@ def test_sampler_transformer_logits_and_sampling_loop(cuda, mode):
         ops.set_split_k(**old)
     # (in fp16 mode an fp32-ulp change of the stream can flip an fp16 rounding downstream)
     assert _rel(got_sk, want) < _tol(mode) and _rel(got_sk, got) < (1e-4 if mode == "fp32" else _tol(mode))
+    # own-head path of the sampling loop: positions grouped by texture, one batched GEMM against each group's
+    # own head -- the same numbers as the all-heads logits gathered at the own head, bit for bit
+    for tex_case in (tex, torch.full_like(tex, 5), torch.where(tex < 9, tex, torch.full_like(tex, 20))):
+        tc = tex_case.clamp(0, 17)
+        dest, rows = s.sampler_fn.group_by_texture(tc, 18)
+        assert rows % 128 == 0 and int(dest.max()) < 18 * rows and dest.unique().numel() == B * T
+        hf = torch.zeros((ops.get_terms(), 18 * rows, 512), dtype=torch.float16, device=cuda)
+        own = s.sampler_fn.forward_own_logits(idx, segm, tc, dest, hf)
+        full = s.sampler_fn.forward_logits(idx, segm, tc)
+        want_own = full.gather(2, tc.view(B, T, 1, 1).expand(B, T, 1, 1024)).view(B * T, 1024)
+        assert torch.equal(own, want_own)
     if mode == "fp32":
         mask = R.blocky_mask(4, B, 512, 256, 64).to(cuda)
         gen = torch.Generator(device=cuda).manual_seed(2021)

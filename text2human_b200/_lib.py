@@ -67,6 +67,7 @@ SIGNATURES = {
     "t2h_onehot_to_planes": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "t2h_embed_sum": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "t2h_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
+    "t2h_layernorm_scatter": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P, _L, _P]),
     "t2h_pack_u8": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "t2h_argmax_heads": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_f32_to_planes_t": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),

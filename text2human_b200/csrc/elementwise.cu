@@ -331,7 +331,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, __half* __restr
 template <int PER_LANE>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __half* __restrict__ out,
-                                 long long rows, int C, float eps, int terms, long long plane) {
+                                 long long rows, int C, float eps, int terms, long long plane,
+                                 const long long* __restrict__ row_map) {
   pdl_launch_dependents();
   pdl_wait();  // before any early return: a grid none of whose CTAs wait could finish before its predecessor
   const int warps = blockDim.x >> 5;
@@ -339,6 +340,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* src = x + row * C;
+  const long long orow = row_map ? row_map[row] : row;  // scatter: the grouped-head GEMM wants rows by texture
   float v[PER_LANE];
   float sum = 0.f;
 #pragma unroll
@@ -366,8 +368,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     if (c < C) {
       __half hi, lo;
       split_f16((v[i] - mean) * rstd * gamma[c] + beta[c], hi, lo);
-      out[row * C + c] = hi;
-      if (terms == 2) out[plane + row * C + c] = lo;
+      out[orow * C + c] = hi;
+      if (terms == 2) out[plane + orow * C + c] = lo;
     }
   }
 }
@@ -618,9 +620,11 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
   const long long plane = rows * c;
   cudaStream_t st = as_stream(stream);
   if (c <= 512)
-    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane));
+    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane,
+                        static_cast<const long long*>(nullptr)));
   else
-    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane));
+    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane,
+                        static_cast<const long long*>(nullptr)));
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -673,6 +677,26 @@ int t2h_pack_u8(const float* x, uint8_t* out, int n, int c, int h, int w, float 
   const long long total = (long long)n * h * w;
   pack_u8_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, out, c, h * w, total, scale, shift);
   T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_layernorm_scatter(const float* x, const float* gamma, const float* beta, void* out, int64_t rows, int c,
+                          float eps, int terms, const int64_t* row_map, int64_t out_rows, t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && gamma && beta && out && row_map && rows > 0 && c > 0 && out_rows >= rows,
+                "layernorm_scatter: bad args");
+  T2H_CHECK_ARG(c <= 1024 && (terms == 1 || terms == 2), "layernorm_scatter: C=%d terms=%d unsupported", c, terms);
+  const int warps = 4;
+  const int grid = (int)ceil_div64(rows, warps);
+  __half* o = reinterpret_cast<__half*>(out);
+  const long long plane = out_rows * c;
+  const long long* rm = reinterpret_cast<const long long*>(row_map);
+  cudaStream_t st = as_stream(stream);
+  if (c <= 512)
+    T2H_CUDA(launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps,
+                        terms, plane, rm));
+  else
+    T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps,
+                        terms, plane, rm));
   return T2H_OK;
 }
 

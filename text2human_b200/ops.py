@@ -554,6 +554,18 @@ def layer_norm(x, gamma, beta, eps=1e-5, terms=None):
     return out
 
 
+def layer_norm_scatter(x, gamma, beta, out, row_map, eps=1e-5):
+    """LayerNorm of fp32 [rows, C]; row r lands in row row_map[r] of the planes buffer out [T, out_rows, C]
+    (rows of ``out`` that no position maps to are left untouched)"""
+    _need_cuda(x, out, row_map)
+    rows, Cc = x.shape
+    assert out.is_contiguous() and out.shape[2] == Cc and row_map.dtype == torch.int64 and row_map.numel() == rows
+    _count(1)
+    _lib.check(_lib.load().t2h_layernorm_scatter(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, Cc, eps,
+                                                 out.shape[0], _ptr(row_map), out.shape[1], _stream()))
+    return out
+
+
 def embed_sum(idx, segm, tex, tok_emb, pos_emb, segm_emb, tex_emb):
     _need_cuda(idx, tok_emb)
     B, T = idx.shape

@@ -232,21 +232,29 @@ class Sampler(nn.Module):
         self.sample_steps = opt['sample_steps']
         self._graphs = {}
 
-    def _logits_fn(self, B, T, device, use_graph):
-        """the transformer forward for fixed (B, T): ~240 small launches per step are CPU-launch-bound, so
-        they are captured once into a CUDA graph and replayed every diffusion step"""
+    def _own_logits_fn(self, B, T, device, use_graph, rows_per_head):
+        """the transformer forward for fixed (B, T, rows_per_head), returning each position's own-head logits:
+        ~220 small launches per step are CPU-launch-bound, so they are captured once into a CUDA graph and
+        replayed every diffusion step"""
         m = self.sampler_fn
-        if not use_graph:
-            return m.forward_logits
-        key = (B, T, str(device), ops.get_terms(), ops.SPLIT_K["inference"])
-        g = self._graphs.get(key)
-        if g is None:
-            ex = (torch.full((B, T), self.mask_id, dtype=torch.long, device=device),
-                  torch.zeros((B, T), dtype=torch.long, device=device),
-                  torch.zeros((B, T), dtype=torch.long, device=device))
-            g = GraphedStep(m.forward_logits, ex)
-            self._graphs[key] = g
-        return g
+        Tt = ops.get_terms()
+        key = (B, T, str(device), Tt, ops.SPLIT_K["inference"], rows_per_head, use_graph)
+        hit = self._graphs.get(key)
+        if hit is None:
+            # rows no position maps to stay zero for the lifetime of the buffer
+            hf = torch.zeros((Tt, m.num_head * rows_per_head, m.n_embd), dtype=torch.float16, device=device)
+
+            def fn(x_t, segm, tex, dest):
+                return m.forward_own_logits(x_t, segm, tex, dest, hf)
+            if use_graph:
+                ex = (torch.full((B, T), self.mask_id, dtype=torch.long, device=device),
+                      torch.zeros((B, T), dtype=torch.long, device=device),
+                      torch.zeros((B, T), dtype=torch.long, device=device),
+                      torch.arange(B * T, dtype=torch.long, device=device))
+                fn = GraphedStep(fn, ex)
+            hit = (fn, hf)
+            self._graphs[key] = hit
+        return hit
 
     @torch.no_grad()
     def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None, use_graph=True):
@@ -262,15 +270,17 @@ class Sampler(nn.Module):
         unmasked = torch.zeros((B, T), dtype=torch.bool, device=dev)
         nh, ncls = m.num_head, m.head_class_num
         tex_c = tex.clamp(0, nh - 1)
-        gather_idx = tex_c.view(B, T, 1, 1).expand(B, T, 1, ncls)
         valid_tex = (tex >= 0) & (tex < nh)
-        logits_fn = self._logits_fn(B, T, dev, use_graph)
+        # positions grouped by texture once per run: every step's head GEMM then only computes each position's
+        # own head (the reference computes all 18 heads for every position and keeps one)
+        dest, rows_per_head = m.group_by_texture(tex_c, nh)
+        logits_fn, hf = self._own_logits_fn(B, T, dev, use_graph, rows_per_head)
+        hf.zero_()  # padding rows of a previous run's grouping must not leak in (they only cost time, but keep it clean)
         for t in range(steps, 0, -1):
             changes = torch.rand((B, T), device=dev, generator=generator) < (1.0 / t)
             changes = changes & ~unmasked
             unmasked = unmasked | changes
-            logits = logits_fn(x_t, segm_tokens, tex_c)  # [B,T,nh,ncls]
-            own = logits.gather(2, gather_idx).view(B * T, ncls)  # each position's own texture head
+            own = logits_fn(x_t, segm_tokens, tex_c, dest)  # [B*T, ncls]: each position's own texture head
             probs = torch.softmax(own / temp, dim=-1)
             draw = torch.multinomial(probs, 1, True, generator=generator).view(B, T)
             upd = changes & valid_tex

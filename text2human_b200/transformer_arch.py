@@ -190,6 +190,44 @@ class TransformerMultiHead(nn.Module):
         logits = ops.linear(h, self._heads_packed())  # [B*T, num_head*head_class_num]
         return logits.view(B, T, self.num_head, self.head_class_num)
 
+    @staticmethod
+    def group_by_texture(texture_tokens, num_head):
+        """texture ids [B,T] -> (dest int64 [B*T], rows_per_head): position m's row in a [num_head, rows_per_head]
+        grouping by its texture id (ids outside 0..num_head-1 are clamped), each group padded to a multiple of
+        128 rows.  Constant over a sampling run (the texture mask does not change), so it is computed once;
+        ``rows_per_head`` costs one device->host read."""
+        flat = texture_tokens.reshape(-1).clamp(0, num_head - 1)
+        counts = torch.bincount(flat, minlength=num_head)
+        rows = max(128, (int(counts.max().item()) + 127) // 128 * 128)
+        order = torch.argsort(flat, stable=True)
+        start = torch.cumsum(counts, 0) - counts
+        rank = torch.arange(flat.numel(), device=flat.device) - start[flat[order]]
+        dest = torch.empty_like(flat)
+        dest[order] = flat[order] * rows + rank
+        return dest, rows
+
+    @torch.no_grad()
+    def forward_own_logits(self, idx, segm_tokens, texture_tokens, dest, hf_grouped):
+        """-> fp32 [B*T, head_class_num]: each position's logits in its OWN texture head only (all the sampler
+        ever reads, sample_model.py:300-306).  The final LayerNorm scatters the positions into ``hf_grouped``
+        (planes [T, num_head*rows_per_head, C], zero-initialised by the caller) by ``dest`` from
+        ``group_by_texture``; one batched GEMM then multiplies each group by its own head: 1/18th .. 1x of the
+        all-heads GEMM's work depending on how evenly the textures are spread.  Bit-identical to
+        ``forward_logits`` gathered at the own head."""
+        if self.causal:
+            raise NotImplementedError("sampler='autoregressive' is never used by Text2Human")
+        B, T = idx.shape
+        x = ops.embed_sum(idx, segm_tokens, texture_tokens, _f32(self.tok_emb.weight),
+                          _f32(self.pos_emb)[0], _f32(self.segm_emb.weight), _f32(self.texture_emb.weight))
+        for block in self.blocks:
+            x = block.forward_rows(x, B, T)
+        ops.layer_norm_scatter(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), hf_grouped, dest, self.ln_f.eps)
+        Tt, rows_all, Cc = hf_grouped.shape
+        rows = rows_all // self.num_head
+        w = self._heads_packed().view(Tt, self.num_head, self.head_class_num, Cc)
+        out = ops.bmm_nt(hf_grouped.view(Tt, self.num_head, rows, Cc), w)       # [num_head, rows, ncls]
+        return out.view(rows_all, self.head_class_num).index_select(0, dest)
+
     @torch.no_grad()
     def forward(self, idx, segm_tokens, texture_tokens, t=None):
         logits = self.forward_logits(idx, segm_tokens, texture_tokens)
