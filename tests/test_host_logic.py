@@ -86,3 +86,35 @@ def test_recipe_is_deterministic():
     assert all(torch.equal(a[k], b[k]) for k in a)
     m = R.blocky_mask(1, 2, 64, 32, 16, extra_ids=(20,))
     assert m.shape == (2, 1, 64, 32) and set(np.unique(m.numpy())).issubset(set(range(18)) | {20})
+
+
+def test_group_by_texture_places_every_position_once_inside_its_head_group():
+    """host logic of the sampler's own-head GEMM: rows grouped by texture id, groups padded to 128-row tiles"""
+    import torch
+    from text2human_b200.transformer_arch import TransformerMultiHead
+    g = torch.Generator().manual_seed(3)
+    for tex in (torch.randint(0, 18, (4, 512), generator=g), torch.full((2, 512), 7),
+                torch.randint(0, 3, (1, 40), generator=g)):
+        dest, rows = TransformerMultiHead.group_by_texture(tex, 18)
+        flat = tex.reshape(-1)
+        assert rows % 128 == 0 and rows >= int(torch.bincount(flat, minlength=18).max())
+        assert dest.unique().numel() == flat.numel()                      # no two positions share a row
+        assert torch.equal(dest // rows, flat)                            # each inside its own head's group
+        for k in range(18):                                               # groups are filled from their start,
+            r = (dest[flat == k] % rows).sort().values                    # in position order (stable)
+            assert torch.equal(r, torch.arange(r.numel()))
+            assert torch.equal(dest[flat == k], dest[flat == k].sort().values)
+
+
+def test_split_k_switches_and_choice():
+    from text2human_b200 import ops
+    assert ops.SPLIT_K == {"wgrad": True, "inference": False}
+    old = ops.set_split_k(inference=True, wgrad=False)
+    assert ops.SPLIT_K == {"wgrad": False, "inference": True} and old == {"wgrad": True, "inference": False}
+    ops.set_split_k(**old)
+    assert ops.SPLIT_K == old
+    assert ops.wgrad_k_split(512, 512, 8192) == 18        # 8 output tiles: up to 148 // 8 slices (the kernel
+                                                          # rounds to 16 slices of 8 chunks)
+    assert ops.wgrad_k_split(18432, 512, 8192) == 0       # 288 tiles already fill the GPU
+    assert ops.wgrad_k_split(2048, 512, 2048) == 4        # fc2 at B=4
+    assert ops.wgrad_k_split(64, 64, 64) == 0             # a single K chunk cannot be split
