@@ -288,13 +288,17 @@ int t2h_planes_transpose(const void* x, void* out, int g, int r, int c, int64_t 
 int t2h_colsum(const float* x, float* out, int64_t rows, int c, t2h_stream_t stream);
 /* exact-erf GELU forward to fp16 planes, and backward da = dg * gelu'(a) (nn.GELU, transformer_arch.py:86) */
 int t2h_gelu_fwd(const float* a, void* out, int64_t n, int terms, t2h_stream_t stream);
-int t2h_gelu_bwd(const float* a, const float* dg, float* da, int64_t n, t2h_stream_t stream);
+int t2h_gelu_bwd(const float* a, const float* dg, float* da, void* da_planes /* optional fp16 planes of da */,
+                 int64_t n, int terms, t2h_stream_t stream);
 /* LayerNorm backward; dx is overwritten or (accumulate=1) added to; dgamma/dbeta are accumulated */
 int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                       float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream);
 /* ds = scale * p * (dp - sum_j dp_j p_j) over the last dim; p as fp16 planes */
 int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
                     t2h_stream_t stream);
+/* the same, written straight to fp16 planes of out_scale*ds (the operand of the dQ / dK GEMMs) */
+int t2h_softmax_bwd_planes(const void* p, const float* dp, void* ds_planes, int64_t rows, int cols, float scale,
+                           int terms, float out_scale, t2h_stream_t stream);
 /* masked multi-head cross-entropy: row m belongs to head[m], target[m] (-1 = ignored), weight w[m]:
  * loss_rows[m] = CE (unweighted), dlogits [rows][nh][ncls] = w*(softmax - onehot) in the own head, 0 elsewhere
  * (F.cross_entropy(ignore_index=-1) over 18 heads, transformer_model.py:250-256) */

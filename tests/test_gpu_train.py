@@ -145,6 +145,8 @@ def test_colsum_gelu_layernorm_softmax_backward_kernels():
     g_ref.backward(dg)
     assert _rel(_join(ops.gelu_fwd(a.detach())), g_ref.detach()) < 2e-6
     assert _rel(ops.gelu_bwd(a.detach(), dg), a.grad) < 1e-5
+    da32, dap = ops.gelu_bwd(a.detach(), dg, want_planes=True)      # fp32 + planes from one pass
+    assert _rel(da32, a.grad) < 1e-5 and _rel(_join(dap), da32) < 1e-6
     # LayerNorm backward, overwrite and accumulate, C <= 512 and > 512 paths
     for Cn in (96, 512, 640):
         xx = torch.randn(M, Cn, device=DEV, requires_grad=True)
@@ -169,6 +171,8 @@ def test_colsum_gelu_layernorm_softmax_backward_kernels():
         p = F.softmax(s * scale, -1)
         p.backward(dp)
         ds = ops.softmax_bwd(ops.split_planes(p.detach(), 2), dp, scale)
+        dsp = ops.softmax_bwd_planes(ops.split_planes(p.detach(), 2), dp, scale, out_scale=256.0)
+        assert dsp.shape == (2, 6, 5, cols) and _rel(_join(dsp) / 256.0, ds) < 1e-6
         assert _rel(ds, s.grad) < 1e-5, cols
 
 

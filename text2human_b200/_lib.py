@@ -74,7 +74,8 @@ SIGNATURES = {
     "t2h_planes_transpose": (_I, [_P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _P]),
     "t2h_colsum": (_I, [_P, _P, _L, _I, _P]),
     "t2h_gelu_fwd": (_I, [_P, _P, _L, _I, _P]),
-    "t2h_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "t2h_gelu_bwd": (_I, [_P, _P, _P, _P, _L, _I, _P]),
+    "t2h_softmax_bwd_planes": (_I, [_P, _P, _P, _L, _I, _F, _I, _F, _P]),
     "t2h_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "t2h_softmax_bwd": (_I, [_P, _P, _P, _L, _I, _F, _I, _P]),
     "t2h_ce_heads": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),

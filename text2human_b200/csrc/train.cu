@@ -146,13 +146,20 @@ __global__ void gelu_fwd_kernel(const float* __restrict__ a, __half* __restrict_
   }
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dg,
-                                float* __restrict__ da, long long n) {
+                                float* __restrict__ da, long long n, __half* __restrict__ da_planes, int terms) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float x = a[i];
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    da[i] = dg[i] * (cdf + x * pdf);
+    const float g = dg[i] * (cdf + x * pdf);
+    da[i] = g;  // fp32 copy for the bias gradient (colsum)
+    if (da_planes) {
+      __half hi, lo;
+      split_f16(g, hi, lo);
+      da_planes[i] = hi;
+      if (terms == 2) da_planes[n + i] = lo;
+    }
   }
 }
 
@@ -258,7 +265,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 template <int PAIRS>
 __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __restrict__ dp,
                                    float* __restrict__ ds, long long rows, int cols, float scale, int terms,
-                                   long long plane) {
+                                   long long plane, __half* __restrict__ ds_planes, float out_scale) {
   const int warps = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -293,7 +300,19 @@ __global__ void softmax_bwd_kernel(const __half* __restrict__ p, const float* __
 #pragma unroll
   for (int i = 0; i < PAIRS; ++i) {
     const int c = lane + i * 32;
-    if (c < npairs) dsr[c] = make_float2(scale * pv[i].x * (dv[i].x - dot), scale * pv[i].y * (dv[i].y - dot));
+    if (c < npairs) {
+      const float a = scale * pv[i].x * (dv[i].x - dot), b = scale * pv[i].y * (dv[i].y - dot);
+      if (ds_planes) {
+        // straight to the fp16 planes (x out_scale) the dQ / dK GEMMs consume: no fp32 round trip
+        __half h0, l0, h1, l1;
+        split_f16(a * out_scale, h0, l0);
+        split_f16(b * out_scale, h1, l1);
+        reinterpret_cast<__half2*>(ds_planes + row * cols)[c] = __halves2half2(h0, h1);
+        if (terms == 2) reinterpret_cast<__half2*>(ds_planes + plane + row * cols)[c] = __halves2half2(l0, l1);
+      } else {
+        dsr[c] = make_float2(a, b);
+      }
+    }
   }
 }
 
@@ -423,9 +442,11 @@ int t2h_gelu_fwd(const float* a, void* out, int64_t n, int terms, t2h_stream_t s
   return T2H_OK;
 }
 
-int t2h_gelu_bwd(const float* a, const float* dg, float* da, int64_t n, t2h_stream_t stream) {
-  T2H_CHECK_ARG(a && dg && da && n > 0, "gelu_bwd: bad args");
-  gelu_bwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(a, dg, da, n);
+int t2h_gelu_bwd(const float* a, const float* dg, float* da, void* da_planes, int64_t n, int terms,
+                 t2h_stream_t stream) {
+  T2H_CHECK_ARG(a && dg && da && n > 0 && (!da_planes || terms == 1 || terms == 2), "gelu_bwd: bad args");
+  gelu_bwd_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(a, dg, da, n, reinterpret_cast<__half*>(da_planes),
+                                                                terms);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }
@@ -446,9 +467,24 @@ int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
   return T2H_OK;
 }
 
+static int softmax_bwd_impl(const void* p, const float* dp, float* ds, void* ds_planes, float out_scale, int64_t rows,
+                            int cols, float scale, int terms, t2h_stream_t stream);
+
 int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
                     t2h_stream_t stream) {
-  T2H_CHECK_ARG(p && dp && ds && rows > 0 && cols > 0 && cols <= 2048 && cols % 2 == 0,
+  T2H_CHECK_ARG(ds, "softmax_bwd: null output");
+  return softmax_bwd_impl(p, dp, ds, nullptr, 1.f, rows, cols, scale, terms, stream);
+}
+
+int t2h_softmax_bwd_planes(const void* p, const float* dp, void* ds_planes, int64_t rows, int cols, float scale,
+                           int terms, float out_scale, t2h_stream_t stream) {
+  T2H_CHECK_ARG(ds_planes, "softmax_bwd_planes: null output");
+  return softmax_bwd_impl(p, dp, nullptr, ds_planes, out_scale, rows, cols, scale, terms, stream);
+}
+
+static int softmax_bwd_impl(const void* p, const float* dp, float* ds, void* ds_planes, float out_scale, int64_t rows,
+                            int cols, float scale, int terms, t2h_stream_t stream) {
+  T2H_CHECK_ARG(p && dp && (ds || ds_planes) && rows > 0 && cols > 0 && cols <= 2048 && cols % 2 == 0,
                 "softmax_bwd: bad args (cols must be even and <= 2048)");
   T2H_CHECK_ARG(terms == 1 || terms == 2, "softmax_bwd: terms=%d", terms);
   const int warps = 4;
@@ -456,9 +492,11 @@ int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int
   cudaStream_t st = as_stream(stream);
   const __half* ph = reinterpret_cast<const __half*>(p);
   if (cols <= 512)
-    softmax_bwd_kernel<8><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+    softmax_bwd_kernel<8><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols,
+                                                      reinterpret_cast<__half*>(ds_planes), out_scale);
   else
-    softmax_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols);
+    softmax_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(ph, dp, ds, rows, cols, scale, terms, rows * cols,
+                                                       reinterpret_cast<__half*>(ds_planes), out_scale);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -712,12 +712,15 @@ def gelu_fwd(a, terms=None):
     return out
 
 
-def gelu_bwd(a, dg):
+def gelu_bwd(a, dg, want_planes=False, terms=None):
+    """da = dg * gelu'(a) (fp32) [, and its fp16 planes for the following GEMMs, from the same pass]"""
     _need_cuda(a, dg)
     da = torch.empty_like(a)
+    terms = terms or get_terms()
+    planes = torch.empty((terms,) + tuple(a.shape), dtype=torch.float16, device=a.device) if want_planes else None
     _count(1)
-    _lib.check(_lib.load().t2h_gelu_bwd(_ptr(a), _ptr(dg), _ptr(da), a.numel(), _stream()))
-    return da
+    _lib.check(_lib.load().t2h_gelu_bwd(_ptr(a), _ptr(dg), _ptr(da), _ptr(planes), a.numel(), terms, _stream()))
+    return (da, planes) if want_planes else da
 
 
 def layernorm_bwd_(dx, dy, x, gamma, dgamma, dbeta, eps=1e-5, accumulate=True):
@@ -738,6 +741,18 @@ def softmax_bwd(p, dp, scale):
     _count(1)
     _lib.check(_lib.load().t2h_softmax_bwd(_ptr(p), _ptr(dp), _ptr(ds), rows, cols, scale, p.shape[0], _stream()))
     return ds
+
+
+def softmax_bwd_planes(p, dp, scale, out_scale=1.0):
+    """as softmax_bwd, but out_scale*ds goes straight to fp16 planes [T, ...] (no fp32 round trip)"""
+    _need_cuda(p, dp)
+    cols = dp.shape[-1]
+    rows = dp.numel() // cols
+    out = torch.empty((p.shape[0],) + tuple(dp.shape), dtype=torch.float16, device=dp.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_softmax_bwd_planes(_ptr(p), _ptr(dp), _ptr(out), rows, cols, scale, p.shape[0],
+                                                  out_scale, _stream()))
+    return out
 
 
 def ce_heads(logits, target, head, w):

@@ -214,8 +214,7 @@ class SamplerTrainer:
             ops.colsum_(self.g(fc2.bias), dx)
             self._wgrad(dxo, s["g"], self.g(fc2.weight))                              # dW2 [C,F] = dxo^T g
             d_g = ops.linear(dxo, w["fc2"], w_kn=True)                                # [M,F]  = dxo W2
-            d_a = ops.gelu_bwd(s["pre"], d_g)
-            da = ops.f32_to_planes_rows(d_a)
+            d_a, da = ops.gelu_bwd(s["pre"], d_g, want_planes=True)                   # fp32 (bias grad) + planes
             ops.colsum_(self.g(fc1.bias), d_a)
             self._wgrad(da, s["h2"], self.g(fc1.weight))                              # dW1 [F,C]
             d_h2 = ops.linear(da, w["fc1"], w_kn=True)                                # [M,C]
@@ -230,8 +229,7 @@ class SamplerTrainer:
             d_qkv = torch.empty((M, 3 * C), dtype=torch.float32, device=dx.device)
             ops.mha_pv(s["p"], d_y, B, T, nh, planes_out=False, out=d_qkv[:, 2 * C:], p_mn=True, v_tok=True)  # dV
             dp = ops.mha_scores(d_y, B, T, nh, k=v)                                   # dP = dY V^T
-            ds = ops.softmax_bwd(s["p"], dp, scale)
-            dsp = ops.f32_to_planes_rows(ds, scale=DS).view(-1, B, nh, T, T)
+            dsp = ops.softmax_bwd_planes(s["p"], dp, scale, out_scale=DS)             # planes [Tt,B,nh,T,T] of DS*dS
             ops.mha_pv(dsp, k, B, T, nh, planes_out=False, out=d_qkv[:, :C], alpha=1.0 / DS, v_tok=True)     # dQ
             ops.mha_pv(dsp, q, B, T, nh, planes_out=False, out=d_qkv[:, C:2 * C], alpha=1.0 / DS, p_mn=True,
                        v_tok=True)                                                    # dK = dS^T Q
