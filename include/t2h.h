@@ -293,6 +293,12 @@ int t2h_gelu_bwd(const float* a, const float* dg, float* da, void* da_planes /* 
 /* LayerNorm backward; dx is overwritten or (accumulate=1) added to; dgamma/dbeta are accumulated */
 int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                       float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream);
+/* the same with two optional fused outputs of the updated dx: its fp16 planes [terms][rows][c] (the operand of the
+ * next backward GEMMs) and its column sums, accumulated into dx_colsum[c] (the bias gradient of the linear layer
+ * this dx is the output gradient of) */
+int t2h_layernorm_bwd_fused(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                            float* dbeta, int64_t rows, int c, float eps, int accumulate, void* dx_planes, int terms,
+                            float* dx_colsum, t2h_stream_t stream);
 /* ds = scale * p * (dp - sum_j dp_j p_j) over the last dim; p as fp16 planes */
 int t2h_softmax_bwd(const void* p, const float* dp, float* ds, int64_t rows, int cols, float scale, int terms,
                     t2h_stream_t stream);

@@ -163,6 +163,12 @@ def test_colsum_gelu_layernorm_softmax_backward_kernels():
             want = xx.grad + base if acc_mode else xx.grad
             assert _rel(dx, want) < 1e-5, (Cn, acc_mode)
             assert _rel(dgam, gam.grad) < 1e-5 and _rel(dbet, bet.grad) < 1e-5, (Cn, acc_mode)
+            # fused outputs of the same pass: planes of the updated dx and its column sums (a bias gradient)
+            dx2 = base.clone()
+            cs = torch.ones(Cn, device=DEV)
+            pl = ops.layernorm_bwd_(dx2, dy, xx.detach(), gam.detach(), torch.zeros_like(dgam), torch.zeros_like(dbet),
+                                    1e-5, accumulate=acc_mode, want_planes=True, colsum_out=cs)
+            assert torch.equal(dx2, dx) and _rel(_join(pl), dx) < 1e-6 and _rel(cs, 1 + dx.sum(0)) < 1e-4
     # softmax backward
     for cols in (32, 512, 600):
         s = torch.randn(6, 5, cols, device=DEV, requires_grad=True)

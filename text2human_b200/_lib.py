@@ -75,6 +75,7 @@ SIGNATURES = {
     "t2h_colsum": (_I, [_P, _P, _L, _I, _P]),
     "t2h_gelu_fwd": (_I, [_P, _P, _L, _I, _P]),
     "t2h_gelu_bwd": (_I, [_P, _P, _P, _P, _L, _I, _P]),
+    "t2h_layernorm_bwd_fused": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _I, _P, _P]),
     "t2h_softmax_bwd_planes": (_I, [_P, _P, _P, _L, _I, _F, _I, _F, _P]),
     "t2h_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "t2h_softmax_bwd": (_I, [_P, _P, _P, _L, _I, _F, _I, _P]),

@@ -169,21 +169,27 @@ template <int PER_LANE>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                      const float* __restrict__ gamma, float* __restrict__ dx,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
-                                     float eps, int accumulate) {
-  __shared__ float s_dg[PER_LANE * 32], s_db[PER_LANE * 32];
+                                     float eps, int accumulate, __half* __restrict__ dx_planes, int terms,
+                                     float* __restrict__ dx_colsum) {
+  // optional fused outputs: fp16 planes of the updated dx (the operand of the next backward GEMMs) and its
+  // column sums (the bias gradient of the linear layer whose output this dx is the gradient of)
+  __shared__ float s_dg[PER_LANE * 32], s_db[PER_LANE * 32], s_cs[PER_LANE * 32];
   for (int i = threadIdx.x; i < PER_LANE * 32; i += blockDim.x) {
     s_dg[i] = 0.f;
     s_db[i] = 0.f;
+    s_cs[i] = 0.f;
   }
   __syncthreads();
   const int warps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  float dg_acc[PER_LANE], db_acc[PER_LANE], gam[PER_LANE];
+  float dg_acc[PER_LANE], db_acc[PER_LANE], cs_acc[PER_LANE], gam[PER_LANE];
+  const long long plane = rows * C;
 #pragma unroll
   for (int i = 0; i < PER_LANE; ++i) {
     const int c = lane + i * 32;
     dg_acc[i] = 0.f;
     db_acc[i] = 0.f;
+    cs_acc[i] = 0.f;
     gam[i] = c < C ? gamma[c] : 0.f;
   }
   // each warp walks rows with a grid stride and keeps its dgamma/dbeta partial sums in registers
@@ -239,8 +245,16 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
     for (int i = 0; i < PER_LANE; ++i) {
       const int c = lane + i * 32;
       if (c < C) {
-        const float v = rstd * (gv[i] - m1 - xv[i] * m2);
-        dx[row * C + c] = accumulate ? dx[row * C + c] + v : v;
+        float v = rstd * (gv[i] - m1 - xv[i] * m2);
+        if (accumulate) v += dx[row * C + c];
+        dx[row * C + c] = v;
+        cs_acc[i] += v;
+        if (dx_planes) {
+          __half hi, lo;
+          split_f16(v, hi, lo);
+          dx_planes[row * C + c] = hi;
+          if (terms == 2) dx_planes[plane + row * C + c] = lo;
+        }
       }
     }
   }
@@ -251,12 +265,14 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
     if (c < C) {
       atomicAdd(&s_dg[c], dg_acc[i]);
       atomicAdd(&s_db[c], db_acc[i]);
+      if (dx_colsum) atomicAdd(&s_cs[c], cs_acc[i]);
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     atomicAdd(&dgamma[c], s_dg[c]);
     atomicAdd(&dbeta[c], s_db[c]);
+    if (dx_colsum) atomicAdd(&dx_colsum[c], s_cs[c]);
   }
 }
 
@@ -451,8 +467,26 @@ int t2h_gelu_bwd(const float* a, const float* dg, float* da, void* da_planes, in
   return T2H_OK;
 }
 
+static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                              float* dbeta, int64_t rows, int c, float eps, int accumulate, void* dx_planes, int terms,
+                              float* dx_colsum, t2h_stream_t stream);
+
 int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
                       float* dbeta, int64_t rows, int c, float eps, int accumulate, t2h_stream_t stream) {
+  return layernorm_bwd_impl(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate, nullptr, 1, nullptr, stream);
+}
+
+int t2h_layernorm_bwd_fused(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                            float* dbeta, int64_t rows, int c, float eps, int accumulate, void* dx_planes, int terms,
+                            float* dx_colsum, t2h_stream_t stream) {
+  T2H_CHECK_ARG(!dx_planes || terms == 1 || terms == 2, "layernorm_bwd_fused: terms=%d", terms);
+  return layernorm_bwd_impl(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate, dx_planes, terms, dx_colsum,
+                            stream);
+}
+
+static int layernorm_bwd_impl(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma,
+                              float* dbeta, int64_t rows, int c, float eps, int accumulate, void* dx_planes, int terms,
+                              float* dx_colsum, t2h_stream_t stream) {
   T2H_CHECK_ARG(dy && x && gamma && dx && dgamma && dbeta && rows > 0 && c > 0, "layernorm_bwd: bad args");
   T2H_CHECK_ARG(c <= 1024, "layernorm_bwd: C=%d > 1024 unsupported", c);
   const int warps = 8;
@@ -460,9 +494,11 @@ int t2h_layernorm_bwd(const float* dy, const float* x, const float* gamma, float
   const int grid = (int)(want < 1 ? 1 : want);   // cover HBM latency, 16x fewer global atomics than per-row
   cudaStream_t st = as_stream(stream);
   if (c <= 512)
-    layernorm_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate);
+    layernorm_bwd_kernel<16><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate,
+                                                          reinterpret_cast<__half*>(dx_planes), terms, dx_colsum);
   else
-    layernorm_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate);
+    layernorm_bwd_kernel<32><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, dgamma, dbeta, rows, c, eps, accumulate,
+                                                          reinterpret_cast<__half*>(dx_planes), terms, dx_colsum);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

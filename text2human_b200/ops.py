@@ -723,13 +723,19 @@ def gelu_bwd(a, dg, want_planes=False, terms=None):
     return (da, planes) if want_planes else da
 
 
-def layernorm_bwd_(dx, dy, x, gamma, dgamma, dbeta, eps=1e-5, accumulate=True):
-    """dx (+)= LayerNorm backward of dy wrt x; dgamma/dbeta accumulated"""
+def layernorm_bwd_(dx, dy, x, gamma, dgamma, dbeta, eps=1e-5, accumulate=True, want_planes=False, colsum_out=None,
+                   terms=None):
+    """dx (+)= LayerNorm backward of dy wrt x; dgamma/dbeta accumulated.  Optionally, from the same pass: the
+    fp16 planes of the updated dx (returned) and its column sums accumulated into ``colsum_out`` [C]."""
     _need_cuda(dx, dy, x)
     rows, Cc = x.shape
+    terms = terms or get_terms()
+    planes = torch.empty((terms, rows, Cc), dtype=torch.float16, device=x.device) if want_planes else None
     _count(1)
-    _lib.check(_lib.load().t2h_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
-                                             rows, Cc, eps, 1 if accumulate else 0, _stream()))
+    _lib.check(_lib.load().t2h_layernorm_bwd_fused(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(dx), _ptr(dgamma),
+                                                   _ptr(dbeta), rows, Cc, eps, 1 if accumulate else 0, _ptr(planes),
+                                                   terms, _ptr(colsum_out), _stream()))
+    return planes
 
 
 def softmax_bwd(p, dp, scale):

@@ -199,8 +199,11 @@ class SamplerTrainer:
         d_hf = ops.linear(dl, w_heads, w_kn=True)                        # [M, C] = dlogits W_heads
         del dlogits, dl
         dx = torch.zeros((M, C), dtype=torch.float32, device=x_0.device)  # running gradient of the stream
-        ops.layernorm_bwd_(dx, d_hf, x_last, m.ln_f.weight.detach(), self.g(m.ln_f.weight), self.g(m.ln_f.bias),
-                           m.ln_f.eps, accumulate=False)
+        # every LayerNorm backward also emits what the next stage needs from the dx it just wrote: its fp16
+        # planes and its column sums (the bias gradient of the linear layer that produced that activation)
+        dxo = ops.layernorm_bwd_(dx, d_hf, x_last, m.ln_f.weight.detach(), self.g(m.ln_f.weight), self.g(m.ln_f.bias),
+                                 m.ln_f.eps, accumulate=False, want_planes=True,
+                                 colsum_out=self.g(m.blocks[-1].mlp[2].bias))
         self._bucket_done("head", reduce)
 
         # ---- blocks, last to first; dx is updated in place
@@ -210,19 +213,16 @@ class SamplerTrainer:
             fc1, fc2 = blk.mlp[0], blk.mlp[2]
             q, k, v = s["qkv"][:, :, :C], s["qkv"][:, :, C:2 * C], s["qkv"][:, :, 2 * C:]
             # MLP: x_out = x_mid + fc2(gelu(fc1(ln2(x_mid))))
-            dxo = ops.f32_to_planes_rows(dx)
-            ops.colsum_(self.g(fc2.bias), dx)
             self._wgrad(dxo, s["g"], self.g(fc2.weight))                              # dW2 [C,F] = dxo^T g
             d_g = ops.linear(dxo, w["fc2"], w_kn=True)                                # [M,F]  = dxo W2
             d_a, da = ops.gelu_bwd(s["pre"], d_g, want_planes=True)                   # fp32 (bias grad) + planes
             ops.colsum_(self.g(fc1.bias), d_a)
             self._wgrad(da, s["h2"], self.g(fc1.weight))                              # dW1 [F,C]
             d_h2 = ops.linear(da, w["fc1"], w_kn=True)                                # [M,C]
-            ops.layernorm_bwd_(dx, d_h2, s["x_mid"], blk.ln2.weight.detach(), self.g(blk.ln2.weight),
-                               self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True)   # dx = d x_mid
+            dxm = ops.layernorm_bwd_(dx, d_h2, s["x_mid"], blk.ln2.weight.detach(), self.g(blk.ln2.weight),
+                                     self.g(blk.ln2.bias), blk.ln2.eps, accumulate=True, want_planes=True,
+                                     colsum_out=self.g(a.proj.bias))                  # dx = d x_mid
             # attention output projection: x_mid = x_in + proj(y)
-            dxm = ops.f32_to_planes_rows(dx)
-            ops.colsum_(self.g(a.proj.bias), dx)
             self._wgrad(dxm, s["y"], self.g(a.proj.weight))                           # dWp [C,C]
             d_y = ops.linear(dxm, w["proj"], w_kn=True, planes_out=True)              # planes [Tt,M,C]
             # attention core; the three gradients land side by side in d_qkv [M, 3C]
@@ -238,8 +238,10 @@ class SamplerTrainer:
             ops.colsum_(self._flat_view(self.flat_g, a.query.bias, 1, 3 * C)[0], d_qkv)
             self._wgrad(dqkv, s["h1"], self._flat_view(self.flat_g, a.query.weight, 3 * C, C))
             d_h1 = ops.linear(dqkv, w["qkv"], w_kn=True)                              # [M,C]
-            ops.layernorm_bwd_(dx, d_h1, s["x_in"], blk.ln1.weight.detach(), self.g(blk.ln1.weight),
-                               self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True)   # dx = d x_in
+            dxo = ops.layernorm_bwd_(dx, d_h1, s["x_in"], blk.ln1.weight.detach(), self.g(blk.ln1.weight),
+                                     self.g(blk.ln1.bias), blk.ln1.eps, accumulate=True, want_planes=li > 0,
+                                     colsum_out=self.g(m.blocks[li - 1].mlp[2].bias) if li > 0 else None)
+            # dx = d x_in = the gradient of the previous layer's output
             saved[li] = None
             if li % self.bucket_layers == 0:
                 hi = min(self.n_layers, li + self.bucket_layers)
