@@ -121,3 +121,12 @@ TINY_FCN = dict(in_channels=8, channels=8, in_index=4, num_convs=1, concat_input
 REAL_UNET = dict(in_channels=256)
 REAL_FCN = dict(in_channels=64, channels=64, in_index=4, num_convs=1, concat_input=False, dropout_ratio=0.1,
                 num_classes=512, align_corners=False, num_head=18)
+
+
+# reduced VQGAN + discriminator for the GAN-training-step fixture (real: configs/vqvae_top.yml, ndf 64, 3 layers)
+TINY_VQGAN_TRAIN = dict(
+    enc=dict(ch=32, num_res_blocks=1, attn_resolutions=[8], in_channels=3, resolution=64, z_channels=32,
+             ch_mult=[1, 2, 2, 4], double_z=False, dropout=0.0),                    # x [B,3,64,32] -> z [B,32,8,4]
+    dec=dict(in_channels=3, resolution=64, z_channels=32, ch=32, out_ch=3, num_res_blocks=1, attn_resolutions=[8],
+             ch_mult=[1, 2, 2, 4], dropout=0.0, resamp_with_conv=True, give_pre_end=False),
+    n_embed=64, embed_dim=32, ndf=16, disc_layers=3, disc_start_step=0, step=5, batch=2)
