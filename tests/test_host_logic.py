@@ -118,3 +118,22 @@ def test_split_k_switches_and_choice():
     assert ops.wgrad_k_split(18432, 512, 8192) == 0       # 288 tiles already fill the GPU
     assert ops.wgrad_k_split(2048, 512, 2048) == 4        # fc2 at B=4
     assert ops.wgrad_k_split(64, 64, 64) == 0             # a single K chunk cannot be split
+
+
+def test_conv_data_gradient_is_a_forward_conv_with_flipped_transposed_weights():
+    """host logic for the conv backward plan: dX of a stride-1 'same' conv equals the forward conv of
+    dY with ops.conv_weight_for_dgrad(W), for 3x3 and 1x1 kernels"""
+    import torch
+    import torch.nn.functional as F
+    from text2human_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for k, cin, cout in ((3, 5, 7), (1, 4, 6)):
+        x = torch.randn(2, cin, 9, 6, generator=g, requires_grad=True)
+        w = torch.randn(cout, cin, k, k, generator=g)
+        dy = torch.randn(2, cout, 9, 6, generator=g)
+        F.conv2d(x, w, padding=k // 2).backward(dy)
+        wd = ops.conv_weight_for_dgrad(w)
+        assert wd.shape == (cin, cout, k, k)
+        got = F.conv2d(dy, wd, padding=k // 2)
+        assert (got - x.grad).abs().max() <= 1e-4 * x.grad.abs().max()
+        assert ops.pack_conv_weight(wd, 2).shape == (2, k * k, cin, (cout + 7) // 8 * 8)

@@ -444,6 +444,14 @@ def pack_conv_weight(w, terms, c_pad=None):
     return split_planes(wt, terms)
 
 
+def conv_weight_for_dgrad(w):
+    """OIHW weight of a stride-1 'same' conv -> the OIHW weight whose FORWARD conv computes that conv's data
+    gradient: dX = conv(dY, W') with W'[ci, co, kh, kw] = W[co, ci, K-1-kh, K-1-kw] (taps flipped, channels
+    exchanged).  With it the data gradient of every 3x3 / 1x1 conv runs on the forward tap-GEMM kernels
+    (DESIGN 10.9); tests/test_host_logic.py checks the identity against autograd."""
+    return w.detach().flip(2, 3).transpose(0, 1).contiguous()
+
+
 def pack_linear_weight(w, terms):
     """[out, in] fp32 (nn.Linear / 1x1 conv weight squeezed) -> planes [T,1,out,in]."""
     w2 = w.detach().float().reshape(w.shape[0], -1)
