@@ -103,27 +103,19 @@ def host_threads():
 
 
 def cpu_port_rate(threads, runs, batch=1):
-    """images/s of the reference path restated in fp32 PyTorch on the host cores (oracle port)"""
-    from oracle import vqgan_ref
+    """images/s of the reference path on the host cores: the reference's own modules when staged (oracle/_ref),
+    else the oracle port.  -> (best, mean, times, kind)"""
     import golden_recipes as R
-    from text2human_b200.pipeline import VQImageSegmTextureModel
-    torch.set_num_threads(threads)
-    torch.manual_seed(2021)
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):
-        m = VQImageSegmTextureModel(VQVAE_TOP).eval()
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    cb = torch.stack([e.weight.detach() for e in m.quantize.embedding_list])
+    fn, kind = _reference_forward_fn("cpu", threads)
     x = R.image(2021, batch, 3, 512, 256)
     mask = R.blocky_mask(2021, batch, 512, 256, 32)
     times = []
-    with torch.no_grad():
-        vqgan_ref.vq_forward_step(sd, cb, x, mask)  # warm-up
-        for _ in range(runs):
-            t0 = time.perf_counter()
-            vqgan_ref.vq_forward_step(sd, cb, x, mask)
-            times.append(time.perf_counter() - t0)
-    return batch / min(times), batch / (sum(times) / len(times)), times
+    fn(x, mask)  # warm-up
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        fn(x, mask)
+        times.append(time.perf_counter() - t0)
+    return batch / min(times), batch / (sum(times) / len(times)), times, kind
 
 
 HIER_OPT = dict(embed_dim=256, n_embed=1024, codebook_spatial_size=2, bot_n_embed=512, bot_double_z=False,
@@ -272,40 +264,128 @@ def train_workload(dev, precision, world, batch=16, steps=4):
                 if world > 1 else "none (1 GPU)", params=tr.flat_p.numel())
 
 
+def _reference_forward_fn(device, threads=None):
+    """-> (fn(x, mask) running the reference's own VQImageSegmTextureModel.forward_step, kind): the UNMODIFIED
+    reference sources staged in oracle/_ref (kind "reference"), else the oracle port (kind "port")."""
+    import contextlib
+    from oracle import ref_loader as RL
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(2021)
+    if RL.available():
+        ns = RL.install("reference", wrappers=("vqgan_model",))
+        w = RL.vq_top_wrapper(ns, VQVAE_TOP, device)
+        for n in w.modules:
+            getattr(w, n).eval()
+
+        def fn(x, mask):
+            with torch.no_grad():
+                return w.forward_step(x, mask)
+        return fn, "reference"
+    from oracle import vqgan_ref
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+    with contextlib.redirect_stdout(sys.stderr):
+        m = VQImageSegmTextureModel(VQVAE_TOP).eval()
+    sd = {k: v.detach().to(device) for k, v in m.state_dict().items()}
+    cb = torch.stack([e.weight.detach() for e in m.quantize.embedding_list]).to(device)
+
+    def fn(x, mask):
+        with torch.no_grad():
+            r = vqgan_ref.vq_forward_step(sd, cb, x, mask)
+        return r["dec"], r["loss"]
+    return fn, "port"
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU path (PyTorch fp32, oracle port), rank 0 only."""
+    """--impl reference: the reference's own implementation of the path (models/vqgan_model.py forward_step around
+    models/archs/vqgan_arch.py, loaded unmodified from oracle/_ref) on the host cores, rank 0 only."""
     if rank != 0:
         return None
     threads = host_threads()
-    from oracle import vqgan_ref
     import golden_recipes as R
-    from text2human_b200.pipeline import VQImageSegmTextureModel
-    torch.set_num_threads(threads)
-    torch.manual_seed(2021)
-    import contextlib
-    with contextlib.redirect_stdout(sys.stderr):
-        m = VQImageSegmTextureModel(VQVAE_TOP).eval()
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    cb = torch.stack([e.weight.detach() for e in m.quantize.embedding_list])
+    fn, kind = _reference_forward_fn("cpu", threads)
     x = R.image(2021, 1, 3, 512, 256)
     mask = R.blocky_mask(2021, 1, 512, 256, 32)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
-            vqgan_ref.vq_forward_step(sd, cb, x, mask)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            vqgan_ref.vq_forward_step(sd, cb, x, mask)
-        total = time.perf_counter() - t0
+    for _ in range(max(1, min(args.warmup, 2))):
+        fn(x, mask)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn(x, mask)
+    total = time.perf_counter() - t0
     value = args.steps / total
     line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="vqvae_top.yml enc-quant-dec 512x256, CPU port of the reference path",
+                config=dict(workload="vqvae_top.yml enc-quant-dec 512x256, the reference's own PyTorch CPU path",
                             step="1 image (bounded sample of the batch-16 workload)"),
-                cpu_baseline=dict(value=value, unit="img/s", cores=threads, kind="port",
+                cpu_baseline=dict(value=value, unit="img/s", cores=threads, kind=kind,
                                   sample=f"{args.steps} steps x 1 image 512x256, torch fp32, {threads} threads"),
                 e2e=dict(value=value, unit="img/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     return line
+
+
+def gpu_eager_baseline(dev, batch=16, steps=3):
+    """BASELINE.md 5.5 / SURVEY 8d: the reference modules themselves on this B200 in stock PyTorch eager (cuDNN /
+    cuBLAS), fp32 with TF32 off and with TF32 allowed, CUDA-event timed -- the bar the hand-written kernels have to
+    beat (a baseline leg like cpu_baseline: none of it is on the product path)."""
+    import golden_recipes as R
+    out = {}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        fn, kind = _reference_forward_fn(dev)
+        x = R.image(2021, batch, 3, 512, 256).to(dev)
+        mask = R.blocky_mask(2021, batch, 512, 256, 32).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for name, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for _ in range(2):
+                fn(x, mask)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                fn(x, mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[f"config2_{name}"] = dict(img_per_s=batch / (ms / 1e3), ms_per_step=ms, batch=batch, kind=kind)
+        del fn, x, mask
+        torch.cuda.empty_cache()
+        # config 4: one transformer forward (= one diffusion step's model call) at B=4
+        from oracle import ref_loader as RL
+        cfg = {k: v for k, v in SAMPLER_OPT.items() if k != "sample_steps"}
+        torch.manual_seed(4)
+        if RL.available():
+            ns = RL.install("reference", wrappers=())
+            net = ns.transformer_arch.TransformerMultiHead(**cfg).to(dev).eval()
+        else:
+            net = None
+        if net is not None:
+            idx = torch.full((4, 512), 18432, dtype=torch.long, device=dev)
+            segm = torch.randint(0, 1024, (4, 512), device=dev)
+            tex = torch.randint(0, 18, (4, 512), device=dev)
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad():
+                    for _ in range(3):
+                        net(idx, segm, tex)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(10):
+                        net(idx, segm, tex)
+                    e1.record()
+                    torch.cuda.synchronize()
+                out[f"config4_{name}"] = dict(ms_per_forward=e0.elapsed_time(e1) / 10, batch=4,
+                                              note="model forward only; the reference's sample_fn adds 18 Categorical "
+                                                   "draws and ~18 host syncs per step on top")
+            del net
+            torch.cuda.empty_cache()
+    except Exception as exc:
+        out["error"] = repr(exc)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
 
 
 class StdoutToStderr:
@@ -485,6 +565,16 @@ def run():
             extra["sampler_train_step"] = train_workload(dev, args.precision, 1)
         except Exception as exc:
             extra["sampler_train_step"] = dict(error=repr(exc))
+    eager = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        eager = gpu_eager_baseline(dev, batch=B)
+        for k in ("config2_fp32", "config2_tf32"):
+            if k in eager:
+                eager[k]["ours_over_eager"] = value / eager[k]["img_per_s"]
+        if extra and "config4_sampler" in extra:
+            for k in ("config4_fp32", "config4_tf32"):
+                if k in eager:
+                    eager[k]["ours_ms_per_step"] = extra["config4_sampler"]["ms_per_diffusion_step"]
     if world > 1 and args.extra_train_ddp:  # opt-in: a collective runs inside (every rank takes part)
         tw = train_workload(dev, args.precision, world)
         extra = dict(sampler_train_step=tw) if rank == 0 else None
@@ -497,10 +587,10 @@ def run():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
-            best, mean, times = cpu_port_rate(threads, runs=3)
-            cpu = dict(value=best, unit="img/s", cores=threads, kind="port",
-                       sample=f"best of 3 runs of 1 image 512x256 (mean {mean:.3f} img/s), torch fp32 oracle "
-                              f"port of the reference path, {threads} threads")
+            best, mean, times, kind = cpu_port_rate(threads, runs=3)
+            cpu = dict(value=best, unit="img/s", cores=threads, kind=kind,
+                       sample=f"best of 3 runs of 1 image 512x256 (mean {mean:.3f} img/s), torch fp32, the "
+                              f"reference's own modules (oracle/_ref) when kind == 'reference', {threads} threads")
         line = dict(metric=METRIC, value=value, unit="img/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32 (fp16x3 split products, fp32 accumulate)" if args.precision == "fp32"
@@ -514,7 +604,7 @@ def run():
                     clocks=clk,
                     e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, extra=extra,
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, extra=extra,
                     pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
                     pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
     if world > 1:

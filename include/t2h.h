@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define T2H_VERSION 100
+#define T2H_VERSION 200
 
 #define T2H_OK 0
 #define T2H_EINVAL (-1)   /* bad argument / unsupported shape            */
@@ -70,7 +70,7 @@ int t2h_device_info(int* cc_major, int* cc_minor, int* num_sms);
  * row-major GEMM (multi-head attention: h = batch, img = head).
  * Accumulation is fp32 in tensor memory.
  * ---------------------------------------------------------------------- */
-#define T2H_MAX_TAPS 9
+#define T2H_MAX_TAPS 16   /* 3x3 convs use 9; the Discriminator's 4x4 convs (vqgan_arch.py:1160-1197) 16 */
 
 #define T2H_OUT_F32 0        /* fp32 output                                  */
 #define T2H_OUT_PLANES 1     /* fp16 planes output (d_terms planes)          */
@@ -82,6 +82,7 @@ int t2h_device_info(int* cc_major, int* cc_minor, int* num_sms);
 #define T2H_ACT_NONE 0
 #define T2H_ACT_GELU 1       /* exact erf GELU, nn.GELU() transformer_arch.py:86 */
 #define T2H_ACT_RELU 2       /* ConvModule's ReLU in the index-prediction UNet / FCN head (unet_arch.py:160) */
+#define T2H_ACT_LRELU 3      /* nn.LeakyReLU(0.2) of the Discriminator (vqgan_arch.py:1163,1180,1195) */
 
 typedef struct t2h_tapgemm_params {
   /* ---- A operand (activations) ---- */
@@ -141,6 +142,9 @@ typedef struct t2h_tapgemm_params {
                             few output tiles, contraction over all tokens) or the residual stream itself
                             (x += proj(y) at small batch).  Needs a 16-byte-aligned fp32 D and no row bias /
                             act / residual / gn_stats.  0/1: off (D is overwritten)                     */
+  int32_t use_tap_w;     /* 1: tap i reads weight slot tap_w[i] of B instead of slot i (the data gradient of a
+                            strided conv uses a subset of the taps per output parity, in place)          */
+  int32_t tap_w[T2H_MAX_TAPS];
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
@@ -184,7 +188,9 @@ int t2h_f32_to_planes(const float* x, void* out, int n, int h, int w, int c,
  * by the caller (or produced by t2h_tapgemm's gn_stats epilogue instead). */
 int t2h_gn_stats(const float* x, double* stats, int n, int hw, int c, int groups,
                  t2h_stream_t stream);
-/* y = gn(x)*gamma+beta, optionally * sigmoid(.)  -> fp16 planes NHWC */
+/* y = act(gn(x)*gamma+beta) -> fp16 planes NHWC; swish: 0 none, 1 swish (nonlinearity(), :513-517), 2 LeakyReLU(0.2).
+ * With n = 1, hw = N*H*W and groups = c the same two kernels are BatchNorm2d in training mode (batch statistics,
+ * eps 1e-5) of the Discriminator (vqgan_arch.py:1178,1193). */
 int t2h_gn_apply(const float* x, const double* stats, const float* gamma,
                  const float* beta, void* out, int n, int hw, int c, int groups,
                  float eps, int swish, int terms, t2h_stream_t stream);
@@ -316,6 +322,87 @@ int t2h_embed_bwd(const float* dx, const int64_t* idx, float* de, int64_t rows, 
 /* torch.optim.Adam step (weight_decay 0); g is multiplied by grad_scale first (1/world after a sum all-reduce) */
 int t2h_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
              float eps, int step, float grad_scale, t2h_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Training step of the VQGAN (VQImageSegmTextureModel.training_step / optimize_parameters,
+ * models/vqgan_model.py:444-488, :329-344; models/losses/vqgan_loss.py; loss.backward()).
+ * Conv data gradients are t2h_tapgemm launches on the transposed weight planes with negated taps; these are
+ * the remaining pieces.
+ * ---------------------------------------------------------------------- */
+/* Conv weight gradient (what autograd computes for nn.Conv2d.weight, vqgan_arch.py:526,548,573-590,840-1197):
+ *   dw[tap][co][ci] += alpha * sum_{n,h,w} dy[n,h,w,co] * x[n + tap_img_off, h + tap_dy, w + tap_dx, ci]
+ * dy, x: NHWC fp16 planes (channel stride 1; plane p of dy / x starts dy_term_imgs / x_term_imgs images after
+ * plane 0); reads of x outside (x_H, x_W) are zero (= the conv's padding); tap_img_off addresses the phases of a
+ * space-to-depth input (stride-2 convs).  dw is accumulated (TMA reduce-add) -- zero it first. */
+typedef struct t2h_conv_wgrad_params {
+  const void* dy;
+  int32_t dy_terms, dy_term_imgs, dy_imgs;
+  int32_t n_img, H, W, cout;          /* extents of dy's (img, h, w, c) dims                          */
+  int64_t dy_sw, dy_sh, dy_sn;        /* element strides of dy                                        */
+  const void* x;
+  int32_t x_terms, x_term_imgs, x_imgs;
+  int32_t x_H, x_W, cin;
+  int64_t x_sw, x_sh, x_sn;
+  int32_t ntaps;
+  int32_t tap_dy[T2H_MAX_TAPS], tap_dx[T2H_MAX_TAPS], tap_img_off[T2H_MAX_TAPS];
+  float* dw;                          /* fp32 [ntaps][cout][dw_ld >= cin]                             */
+  int64_t dw_tap_stride, dw_ld;
+  float alpha;
+  int32_t nterms;                     /* 1 or 3 tensor-core products, as t2h_tapgemm                  */
+  int32_t k_split;                    /* 0: choose so that the GPU is filled                          */
+} t2h_conv_wgrad_params;
+int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t stream);
+
+/* Backward of y = act(norm(x)*gamma + beta) for GroupNorm(groups) per image (Normalize(), vqgan_arch.py:510) or,
+ * with n = 1 / hw = N*H*W / groups = c, training-mode BatchNorm2d.  stats as t2h_gn_stats / the conv epilogue
+ * produced them.  dx = add (optional) + dL/dx; optional fp16 planes of dx; dgamma/dbeta accumulated (may be NULL).
+ * ws: 2*n*c doubles of scratch.  act: 0 none, 1 swish, 2 LeakyReLU(0.2). */
+int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
+                 const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
+                 int n, int hw, int c, int groups, float eps, int act, t2h_stream_t stream);
+/* BatchNorm2d running statistics: r = (1-momentum) r + momentum * batch (unbiased variance); stats [c][2] */
+int t2h_bn_update_running(const double* stats, float* running_mean, float* running_var, int64_t count,
+                          float momentum, int c, t2h_stream_t stream);
+/* dpre = dy * (y > 0 ? 1 : 0.2), y = LeakyReLU(pre) given by (the hi plane of) its fp16 planes; optional planes */
+int t2h_lrelu_bwd(const void* y_planes, const float* dy, float* dpre, void* dpre_planes, int terms, int64_t n,
+                  t2h_stream_t stream);
+/* fp16 planes [terms][n][h][w][c] -> 4-phase space-to-depth planes [terms][4][n][h/2][w/2][c] (T2H_CVT_S2D's layout),
+ * the operand of the stride-2 convs when the producer already wrote planes (Discriminator, vqgan_arch.py:1160-1180) */
+int t2h_planes_s2d(const void* x, void* out, int terms, int n, int h, int w, int c, t2h_stream_t stream);
+/* adjoint of F.interpolate(scale_factor=2, mode='nearest') (Upsample, :530): x [n,2h,2w,c] -> out [n,h,w,c] */
+int t2h_sumpool2(const float* x, float* out, int n, int h, int w, int c, t2h_stream_t stream);
+/* Quantizer backward (straight-through + legacy-beta loss, vqgan_arch.py:270-281): dz = dzq + coef_z (z - e),
+ * dcodebook[book][idx] += coef_e (e - z); rows whose book_id selects no codebook have e = 0 */
+int t2h_vq_bwd(const float* z, const float* codebook, const int64_t* idx, const int32_t* book_id, const float* dzq,
+               float* dz, float* dcodebook, int64_t rows, int d, int n_books, int n_e, float coef_z, float coef_e,
+               t2h_stream_t stream);
+/* sum[0] += sum |x - xrec|; grad (may be NULL) = gscale * sign(xrec - x)   (torch.abs, vqgan_model.py:449) */
+int t2h_l1_loss(const float* x, const float* xrec, float* grad, double* sum, int64_t n, float gscale,
+                t2h_stream_t stream);
+/* sgn = +1 / -1: sum += relu(1 - sgn*l), grad = -sgn*gscale where positive (hinge_d_loss, vqgan_loss.py:21-26);
+ * sgn = 0: sum += l, grad = gscale (g_loss = -mean(logits_fake), vqgan_model.py:461) */
+int t2h_hinge_loss(const float* logits, float* grad, double* sum, int64_t n, float sgn, float gscale,
+                   t2h_stream_t stream);
+/* DiffAugment(x, 'color,translation') (vqgan_loss.py:29-80) on fp32 NCHW [b,3,h,w]; r [b][3] the brightness /
+ * saturation / contrast uniforms, t [b][2] the integer translations (drawn by the caller in the reference's
+ * order); ssum / dsum: b doubles of scratch */
+int t2h_diffaug_fwd(const float* x, const float* r, const int32_t* t, double* ssum, float* out, int b, int h, int w,
+                    t2h_stream_t stream);
+int t2h_diffaug_bwd(const float* dout, const float* r, const int32_t* t, double* dsum, float* dx, int b, int h,
+                    int w, t2h_stream_t stream);
+/* out[0] = clamp(|rg| / (|gg| + 1e-4), 0, wmax) * enable, gradients scaled by 1/inv_scale
+ * (calculate_adaptive_weight, vqgan_loss.py:5-12) */
+int t2h_adaptive_weight(const float* rg, const float* gg, int64_t n, float inv_scale, float wmax, float enable,
+                        float* out, t2h_stream_t stream);
+/* out = a + w[0]*b with w on the device */
+int t2h_axpy_dev(const float* a, const float* b, const float* w, float* out, int64_t n, t2h_stream_t stream);
+
+/* One reveal step of BaseSampleModel.sample_fn (sample_model.py:283-317): rows with u < inv_t that are still masked
+ * draw a token from softmax(logits[row] * inv_temp) (their own texture head's logits [rows][ncls]; Gumbel-max with
+ * Philox4x32-10 keyed by (seed, step, row, class)) and write x_t[row] = token + cont_stride * tex[row]. */
+int t2h_sample_step(const float* logits, const float* u, const int64_t* tex, int64_t* x_t, uint8_t* unmasked,
+                    int64_t rows, int ncls, int n_heads, float inv_t, float inv_temp, uint64_t seed, uint32_t step,
+                    int64_t cont_stride, t2h_stream_t stream);
 
 #ifdef __cplusplus
 }

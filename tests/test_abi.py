@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.t2h_version() == 100
+    assert lib.t2h_version() == 200
     assert isinstance(lib.t2h_last_error(), bytes)
 
 
@@ -42,9 +42,11 @@ def test_struct_layout_matches_header():
 #include "t2h.h"
 #include <stdio.h>
 #include <stddef.h>
-int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(t2h_tapgemm_params),
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(t2h_tapgemm_params),
   offsetof(t2h_tapgemm_params,b), offsetof(t2h_tapgemm_params,ntaps), offsetof(t2h_tapgemm_params,d),
-  offsetof(t2h_tapgemm_params,alpha), offsetof(t2h_tapgemm_params,gn_cpg)); return 0; }
+  offsetof(t2h_tapgemm_params,alpha), offsetof(t2h_tapgemm_params,gn_cpg),
+  sizeof(t2h_conv_wgrad_params), offsetof(t2h_conv_wgrad_params,x), offsetof(t2h_conv_wgrad_params,ntaps),
+  offsetof(t2h_conv_wgrad_params,dw), offsetof(t2h_conv_wgrad_params,k_split)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "s.c")
@@ -53,7 +55,9 @@ int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(t2h_tapgemm_params),
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         got = [int(v) for v in subprocess.check_output([exe]).split()]
     P = _lib.TapGemmParams
-    want = [ctypes.sizeof(P), P.b.offset, P.ntaps.offset, P.d.offset, P.alpha.offset, P.gn_cpg.offset]
+    W = _lib.ConvWgradParams
+    want = [ctypes.sizeof(P), P.b.offset, P.ntaps.offset, P.d.offset, P.alpha.offset, P.gn_cpg.offset,
+            ctypes.sizeof(W), W.x.offset, W.ntaps.offset, W.dw.offset, W.k_split.offset]
     assert got == want
 
 

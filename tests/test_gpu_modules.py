@@ -149,10 +149,11 @@ def test_vq_pipeline_config1_matches_oracle(cuda):
     dec, loss, info = m.forward_step(x, mask, return_info=True)
     z = info["z_nhwc"].permute(0, 3, 1, 2)
     assert _rel(z, want["z"]) < TOL_EXACT
-    agree = (info["idx_cont"] == want["idx_cont"]).float().mean().item()
-    assert agree >= 0.99, f"only {agree:.4f} of end-to-end indices agree"
-    if agree == 1.0:
-        assert _rel(dec, want["dec"]) < TOL_EXACT
+    from test_gpu_baseline_configs import check_flips   # every differing index must be a near-tie the z error explains
+    ok = check_flips("config1", z, want["z"], cb.to(cuda), info["idx_cont"], want["idx_cont"], 1024)
+    assert bool(ok.any())
+    if bool(ok.all()):   # single image: the end-to-end comparison needs a flip-free image (teacher-forced check below
+        assert _rel(dec, want["dec"]) < TOL_EXACT    # covers the decoder unconditionally); flip count is printed
     # teacher-forced decode: identical quantized input -> pixels within 1e-3
     dec_tf = m.decode(want["quant"])
     with torch.no_grad():
@@ -190,11 +191,17 @@ def test_hierarchy_forward_step_matches_oracle(cuda):
     with torch.no_grad():
         want = vqgan_ref.hierarchy_forward_step(sd, cbt.to(cuda), cbb.to(cuda), x, mask)
     dec, loss, info = m.forward_step(x, mask, return_info=True)
-    top_ok = (info["top_idx"] == want["top_idx"]).float().mean().item()
-    bot_ok = (info["bot_idx"].reshape(-1) == want["bot_idx"].reshape(-1)).float().mean().item()
-    assert top_ok >= 0.98 and bot_ok >= 0.98, (top_ok, bot_ok)
-    if top_ok == 1.0 and bot_ok == 1.0:
-        assert _rel(dec, want["dec"]) < TOL_EXACT
+    from test_gpu_baseline_configs import check_flips
+    from text2human_b200.vqgan_arch import conv1x1_nhwc
+    zt = conv1x1_nhwc(m.top_encoder.forward_nhwc(x), m.top_quant_conv).permute(0, 3, 1, 2)
+    zb = conv1x1_nhwc(m.bot_encoder.forward_nhwc(x), m.bot_quant_conv).permute(0, 3, 1, 2)
+    assert _rel(zt, want["z_top"]) < TOL_EXACT and _rel(zb, want["z_bot"]) < TOL_EXACT
+    ok_t = check_flips("hier-crop top", zt, want["z_top"], cbt.to(cuda), info["top_idx"], want["top_idx"], 1024)
+    ok_b = check_flips("hier-crop bottom", zb, want["z_bot"], cbb.to(cuda), info["bot_idx"], want["bot_idx"], 512, ps=2)
+    img_ok = ok_t.view(2, -1).all(1) & ok_b.view(2, -1).all(1)
+    if bool(img_ok.any()):
+        assert _rel(dec[img_ok], want["dec"][img_ok]) < TOL_EXACT
+    if bool(img_ok.all()):
         assert abs(loss.item() - want["loss"].item()) <= 1e-3 * abs(want["loss"].item())
     # module-level API (NCHW in/out) of the pieces the reference wrapper calls, teacher-forced
     with torch.no_grad():

@@ -10,10 +10,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libt2h.so")
 
-MAX_TAPS = 9
+MAX_TAPS = 16
 OUT_F32, OUT_PLANES = 0, 1
 BIAS_NONE, BIAS_COL, BIAS_ROW = 0, 1, 2
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_LRELU = 0, 1, 2, 3
 CVT_PLAIN, CVT_UP2X, CVT_S2D, CVT_MAXPOOL2, CVT_BILINEAR2X = 0, 1, 2, 3, 4
 
 
@@ -40,6 +40,23 @@ class TapGemmParams(C.Structure):
         ("alpha", C.c_float),
         ("residual", C.c_void_p),
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
+        ("use_tap_w", C.c_int32), ("tap_w", C.c_int32 * MAX_TAPS),
+    ]
+
+
+class ConvWgradParams(C.Structure):
+    """Mirror of ``t2h_conv_wgrad_params`` (include/t2h.h) — field order matters."""
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_terms", C.c_int32), ("dy_term_imgs", C.c_int32), ("dy_imgs", C.c_int32),
+        ("n_img", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("cout", C.c_int32),
+        ("dy_sw", C.c_int64), ("dy_sh", C.c_int64), ("dy_sn", C.c_int64),
+        ("x", C.c_void_p), ("x_terms", C.c_int32), ("x_term_imgs", C.c_int32), ("x_imgs", C.c_int32),
+        ("x_H", C.c_int32), ("x_W", C.c_int32), ("cin", C.c_int32),
+        ("x_sw", C.c_int64), ("x_sh", C.c_int64), ("x_sn", C.c_int64),
+        ("ntaps", C.c_int32),
+        ("tap_dy", C.c_int32 * MAX_TAPS), ("tap_dx", C.c_int32 * MAX_TAPS), ("tap_img_off", C.c_int32 * MAX_TAPS),
+        ("dw", C.c_void_p), ("dw_tap_stride", C.c_int64), ("dw_ld", C.c_int64),
+        ("alpha", C.c_float), ("nterms", C.c_int32), ("k_split", C.c_int32),
     ]
 
 
@@ -82,6 +99,20 @@ SIGNATURES = {
     "t2h_ce_heads": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "t2h_embed_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_adam": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
+    "t2h_conv_wgrad": (_I, [C.POINTER(ConvWgradParams), _P]),
+    "t2h_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "t2h_bn_update_running": (_I, [_P, _P, _P, _L, _F, _I, _P]),
+    "t2h_lrelu_bwd": (_I, [_P, _P, _P, _P, _I, _L, _P]),
+    "t2h_sumpool2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "t2h_planes_s2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "t2h_vq_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _F, _P]),
+    "t2h_l1_loss": (_I, [_P, _P, _P, _P, _L, _F, _P]),
+    "t2h_hinge_loss": (_I, [_P, _P, _P, _L, _F, _F, _P]),
+    "t2h_diffaug_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "t2h_diffaug_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "t2h_adaptive_weight": (_I, [_P, _P, _L, _F, _F, _F, _P, _P]),
+    "t2h_axpy_dev": (_I, [_P, _P, _P, _P, _L, _P]),
+    "t2h_sample_step": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _F, C.c_uint64, C.c_uint32, _L, _P]),
 }
 
 _lib = None

@@ -259,7 +259,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, const double* __res
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float y = f[e] * scale[cc * 8 + e] + shift[cc * 8 + e];
-      if (swish) y = y / (1.0f + __expf(-y));
+      if (swish == 1) y = y / (1.0f + __expf(-y));
+      else if (swish == 2) y = y > 0.f ? y : 0.2f * y;  // LeakyReLU(0.2) (Discriminator BatchNorm path)
       f[e] = y;
     }
     store_split8(f, out, ob + i * 8, plane, terms);

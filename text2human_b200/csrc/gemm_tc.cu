@@ -20,6 +20,7 @@
 // Replaces cuDNN/cuBLAS calls made by the reference modules — see include/t2h.h.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "t2h_internal.h"
 #include "t2h_ptx.cuh"
@@ -55,6 +56,12 @@ struct TapGemmDev {
   const float* residual;
   double* gn_stats;
   int gn_cpg, gn_groups;
+  // conv weight-gradient mode (t2h_conv_wgrad): the contraction runs over 64-pixel patches (wg_PW x wg_PH) of the
+  // images, both operands are NHWC planes read MN-major, the output "image" index is the tap whose (dy, dx,
+  // img_off) shifts the X patch; accum: the epilogue reduce-adds into D even without split-K
+  int wg, accum;
+  int wg_PW, wg_PH, wg_pw, wg_ppi;
+  int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
 };
 
 // profiling scratch (T2H_DEBUG bit 16): per CTA {MMA-thread cycles, MMAs issued, epilogue-warp cycles, tiles}
@@ -249,10 +256,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (P.a_mn) {
                   // [k][row] storage: two boxes of 64 rows x 64 k per 128-row block
                   mbar_expect_tx(&a_full[sa], kABlockBytes);
+                  int c1 = ch * kBK, c2 = t.h0, c3 = a_img + pl * P.a_term_imgs;
+                  if (P.wg) {  // chunk = one 64-pixel patch of dY: (channel, x, y, image)
+                    const int n = ch / P.wg_ppi, r = ch - n * P.wg_ppi, py = r / P.wg_pw, px = r - py * P.wg_pw;
+                    c1 = px * P.wg_PW; c2 = py * P.wg_PH; c3 = n + pl * P.a_term_imgs;
+                  }
 #pragma unroll
                   for (int hbox = 0; hbox < 2; ++hbox)
                     tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot + hbox * 8192, t.w0 + 64 * hbox,
-                                ch * kBK, t.h0, a_img + pl * P.a_term_imgs);
+                                c1, c2, c3);
                 } else {
                   mbar_expect_tx(&a_full[sa], slab_bytes);
                   tma_load_4d(&tmA, &a_full[sa], a_ring + sa * C::kASlot, ch * kBK, t.w0 + P.g_dx[g],
@@ -304,9 +316,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                   } else if (P.b_mn) {
                     // [k][column] storage: one box of 64 columns x 64 k per 64 output columns
+                    int c1 = ch * kBK, c2 = b_g + P.g_btap[g][tp] + pl * P.b_term_g, c3 = b_g2;
+                    if (P.wg) {  // the same patch of X, shifted by this output tile's tap
+                      const int n = ch / P.wg_ppi, r = ch - n * P.wg_ppi, py = r / P.wg_pw, px = r - py * P.wg_pw;
+                      c1 = px * P.wg_PW + P.wg_dx[t.img]; c2 = py * P.wg_PH + P.wg_dy[t.img];
+                      c3 = n + P.wg_ioff[t.img] + pl * P.b_term_g;
+                    }
                     for (int q = 0; q < BN / 64; ++q)
-                      tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q, ch * kBK,
-                                  b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
+                      tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q, c1, c2, c3);
                   } else {
                     tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
                                 b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
@@ -489,6 +506,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else if (P.act == T2H_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else if (P.act == T2H_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
           }
           if (has_res) {
             mbar_wait(&res_bar[buf], res_par[buf]);
@@ -520,7 +540,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           named_bar_sync(2, 128);  // staging tile complete; residual tile fully consumed
           if (elected) {
-            if (P.ksplit > 1)
+            if (P.ksplit > 1 || P.accum)
               tma_reduce_add_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);  // partial sum of a k-slice
             else
               tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);
@@ -592,6 +612,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (P.act == T2H_ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (P.act == T2H_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -653,6 +676,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if (P.act == T2H_ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (P.act == T2H_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
             }
             if (P.d_mode == T2H_OUT_F32) {
               float* dst = reinterpret_cast<float*>(P.d);
@@ -762,11 +788,13 @@ template <int BN, int MBLK>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                   const CUtensorMap& tmR, const TapGemmDev& P, cudaStream_t stream) {
   using C = Cfg<BN, MBLK>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  int dev = 0;
+  T2H_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {  // per device: the attribute lives in the device's copy of the function
     T2H_CUDA(cudaFuncSetAttribute(tapgemm_kernel<BN, MBLK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
-    configured = true;
+    configured[dev & 63] = true;
   }
   // ring depths: enough bytes in flight to cover the TMA round trip at the tile's consumption rate.
   // With the 3-product split both (hi, lo) slabs of a (group, chunk) are live at once.
@@ -798,11 +826,13 @@ template <int MBLK>
 static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const CUtensorMap& tmR, const TapGemmDev& P, cudaStream_t stream) {
   using C = Cfg<128, MBLK>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};
+  int dev = 0;
+  T2H_CUDA(cudaGetDevice(&dev));
+  if (!configured[dev & 63]) {
     T2H_CUDA(cudaFuncSetAttribute(tapgemm_swap_kernel<MBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kDynSmem));
-    configured = true;
+    configured[dev & 63] = true;
   }
   TapGemmDev Q = P;
   {
@@ -850,6 +880,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   T2H_CHECK_ARG(!p->b_batched_h || p->H == 1 || p->tile_rows, "tapgemm: b_batched_h needs row tiles");
 
   TapGemmDev P;
+  memset(&P, 0, sizeof(P));
   P.n_img = p->n_img; P.H = p->H; P.W = p->W;
   P.n_out = p->n_out; P.C = p->C; P.kchunks = (p->C + kBK - 1) / kBK; P.nterms = p->nterms;
   P.a_term_imgs = p->a_term_imgs; P.a_bcast = p->a_bcast;
@@ -936,7 +967,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
         gmin[g] = gmax[g] = p->tap_dy[i];
       }
       gt_dy[g][P.g_ntaps[g]] = p->tap_dy[i];
-      P.g_btap[g][P.g_ntaps[g]] = i;
+      P.g_btap[g][P.g_ntaps[g]] = p->use_tap_w ? p->tap_w[i] : i;
       P.g_ntaps[g]++;
     }
     int extra = 0;
@@ -1070,6 +1101,89 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   switch (BN) {
     case 16: return launch<16, 1>(tmA, tmB, tmD, tmR, P, s);
     case 32: return launch<32, 1>(tmA, tmB, tmD, tmR, P, s);
+    case 64: return launch<64, 1>(tmA, tmB, tmD, tmR, P, s);
+    case 128: return launch<128, 1>(tmA, tmB, tmD, tmR, P, s);
+    default: return launch<256, 1>(tmA, tmB, tmD, tmR, P, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// t2h_conv_wgrad: dW[tap][co][ci] += alpha * sum_{n,h,w} dY[n,h,w,co] * X[n + ioff(tap), h + dy(tap), w + dx(tap), ci]
+// on the same tcgen05 kernel: both operands are NHWC fp16 planes consumed MN-major (the contraction index -- the
+// pixel -- is the outer dimension of both), the K loop walks 64-pixel patches (one TMA box {64 ch, PW, PH, 1}
+// per operand and patch; the tap is a coordinate shift of the X box, zero-filled outside the image = the conv's
+// padding), one output tile per (tap, 128 couts, BN cins), patches split over the SMs and TMA-reduce-added.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t stream) {
+  T2H_CHECK_ARG(p && p->dy && p->x && p->dw, "conv_wgrad: null operand");
+  T2H_CHECK_ARG(p->n_img > 0 && p->H > 0 && p->W > 0 && p->cout > 0 && p->cin > 0, "conv_wgrad: empty problem");
+  T2H_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= T2H_MAX_TAPS, "conv_wgrad: ntaps=%d", p->ntaps);
+  T2H_CHECK_ARG(p->nterms == 1 || (p->nterms == 3 && p->dy_terms == 2 && p->x_terms == 2),
+                "conv_wgrad: nterms=%d needs hi/lo planes on both operands", p->nterms);
+  T2H_CHECK_ARG(p->cin % 4 == 0 && p->dw_ld % 4 == 0 && p->dw_tap_stride % 4 == 0 &&
+                    reinterpret_cast<uintptr_t>(p->dw) % 16 == 0,
+                "conv_wgrad: dW needs cin %% 4 == 0 and 16-byte aligned rows (cin=%d ld=%lld)", p->cin,
+                (long long)p->dw_ld);
+  TapGemmDev P;
+  memset(&P, 0, sizeof(P));
+  int PW = 16;
+  while (PW > 1 && PW / 2 >= p->W) PW >>= 1;  // narrow images: taller patches
+  const int PH = 64 / PW;
+  P.wg = 1; P.accum = 1;
+  P.wg_PW = PW; P.wg_PH = PH;
+  P.wg_pw = ceil_div(p->W, PW);
+  P.wg_ppi = P.wg_pw * ceil_div(p->H, PH);
+  for (int i = 0; i < p->ntaps; ++i) {
+    P.wg_dy[i] = p->tap_dy[i]; P.wg_dx[i] = p->tap_dx[i]; P.wg_ioff[i] = p->tap_img_off[i];
+  }
+  const long long chunks = (long long)p->n_img * P.wg_ppi;
+  T2H_CHECK_ARG(chunks < (1LL << 24), "conv_wgrad: too many pixel patches");
+  P.n_img = p->ntaps; P.H = 1; P.W = p->cout;
+  P.n_out = p->cin; P.kchunks = (int)chunks; P.C = P.kchunks * kBK; P.nterms = p->nterms;
+  P.a_term_imgs = p->dy_term_imgs; P.b_term_g = p->x_term_imgs;
+  P.a_mn = 1; P.b_mn = 1;
+  P.d = p->dw; P.d_mode = T2H_OUT_F32; P.alpha = p->alpha;
+  P.bias_mode = T2H_BIAS_NONE; P.act = T2H_ACT_NONE;
+  P.TW = 128; P.TH = 1;
+  P.ngroups = 1; P.g_ntaps[0] = 1; P.slab_rows = 1;
+  int BN = p->cin <= 64 ? 64 : (p->cin <= 128 ? 128 : 256);
+  P.tiles_w = ceil_div(p->cout, 128); P.tiles_h = 1;
+  P.n_tiles_n = ceil_div(p->cin, BN);
+  P.total_tiles = p->ntaps * P.tiles_w * P.n_tiles_n;
+  P.epi_mode = EPI_TMA_F32;
+  int ks = p->k_split > 0 ? p->k_split : num_sms() / P.total_tiles;
+  if (ks < 1) ks = 1;
+  if (ks > P.kchunks) ks = P.kchunks;
+  P.kper = ceil_div(P.kchunks, ks);
+  P.ksplit = ceil_div(P.kchunks, P.kper);
+  T2H_CHECK_ARG((long long)P.total_tiles * P.ksplit < (1LL << 31), "conv_wgrad: too many work items");
+  P.total_work = P.total_tiles * P.ksplit;
+
+  CUtensorMap tmA, tmB, tmD, tmR;
+  {
+    uint64_t dims[4] = {(uint64_t)p->cout, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->dy_imgs};
+    uint64_t str[4] = {1, (uint64_t)p->dy_sw, (uint64_t)p->dy_sh, (uint64_t)p->dy_sn};
+    uint32_t box[4] = {64, (uint32_t)PW, (uint32_t)PH, 1};
+    int rc = make_tmap(&tmA, p->dy, 2, 4, dims, str, box, "conv_wgrad dY");
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->x_W, (uint64_t)p->x_H, (uint64_t)p->x_imgs};
+    uint64_t str[4] = {1, (uint64_t)p->x_sw, (uint64_t)p->x_sh, (uint64_t)p->x_sn};
+    uint32_t box[4] = {64, (uint32_t)PW, (uint32_t)PH, 1};
+    int rc = make_tmap(&tmB, p->x, 2, 4, dims, str, box, "conv_wgrad X");
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p->cin, (uint64_t)p->cout, 1, (uint64_t)p->ntaps};
+    uint64_t str[4] = {1, (uint64_t)p->dw_ld, (uint64_t)p->dw_ld * (uint64_t)p->cout, (uint64_t)p->dw_tap_stride};
+    uint32_t box[4] = {32, 128, 1, 1};
+    int rc = make_tmap(&tmD, p->dw, 4, 4, dims, str, box, "conv_wgrad dW");
+    if (rc) return rc;
+  }
+  tmR = tmA;
+  cudaStream_t s = as_stream(stream);
+  switch (BN) {
     case 64: return launch<64, 1>(tmA, tmB, tmD, tmR, P, s);
     case 128: return launch<128, 1>(tmA, tmB, tmD, tmR, P, s);
     default: return launch<256, 1>(tmA, tmB, tmD, tmR, P, s);

@@ -287,6 +287,9 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else if (P.act == T2H_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else if (P.act == T2H_ACT_LRELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.2f * v[i];
         }
         if (has_res) {
           mbar_wait(&res_bar[e], res_par);

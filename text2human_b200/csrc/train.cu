@@ -444,7 +444,8 @@ int t2h_planes_transpose(const void* x, void* out, int g, int r, int c, int64_t 
 
 int t2h_colsum(const float* x, float* out, int64_t rows, int c, t2h_stream_t stream) {
   T2H_CHECK_ARG(x && out && rows > 0 && c > 0, "colsum: bad args");
-  const int rpb = 64;
+  int rpb = 64;
+  if (ceil_div64(rows, rpb) > 16384) rpb = (int)ceil_div64(rows, 16384);  // grid.y limit; conv bias gradients have millions of rows
   dim3 grid(ceil_div(c, 128), (unsigned)ceil_div64(rows, rpb));
   colsum_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, out, rows, c, rpb);
   T2H_LAUNCH_OK();

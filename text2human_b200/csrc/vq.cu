@@ -246,7 +246,9 @@ vq_search_kernel(const float* __restrict__ z, const float* __restrict__ cb, cons
           bi = oi;
         }
       }
-      if (lane == 0) best_s[warp * 4 + i] = bi;
+      // a NaN in z leaves every comparison false: fall back to index 0 (what torch.argmin returns there is an
+      // index too) instead of gathering out of bounds
+      if (lane == 0) best_s[warp * 4 + i] = bi == 0x7fffffff ? 0 : bi;
     }
   } else {
     if (tid < kRT) best_s[tid] = -1;

@@ -13,7 +13,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, CVT_BILINEAR2X, CVT_MAXPOOL2, BIAS_COL, BIAS_NONE, BIAS_ROW, CVT_PLAIN, CVT_S2D, CVT_UP2X,
+from ._lib import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, CVT_BILINEAR2X, CVT_MAXPOOL2, BIAS_COL, BIAS_NONE, BIAS_ROW, CVT_PLAIN, CVT_S2D, CVT_UP2X,
                    OUT_F32, OUT_PLANES, TapGemmParams)
 
 # ----------------------------------------------------------------------------
@@ -90,7 +90,8 @@ _TAPS_3x3 = tuple((kh - 1, kw - 1, 0) for kh in range(3) for kw in range(3))
 def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw, a_sh, a_sn,
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
-             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0):
+             tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0,
+             tap_w=None):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -121,6 +122,10 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.k_split = k_split
     p.bias_sn = bias_sn
     p.a_mn, p.b_mn = a_mn, b_mn
+    if tap_w is not None:
+        p.use_tap_w = 1
+        for i, wi in enumerate(tap_w):
+            p.tap_w[i] = wi
     _count()
     if _PROFILE["on"]:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -821,3 +826,256 @@ def pack_u8(x, scale=1.0, shift=0.0):
     _count(1)
     _lib.check(_lib.load().t2h_pack_u8(_ptr(x), _ptr(out), N, Cc, H, W, scale, shift, _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------
+# VQGAN training step: generic tap convolution (forward and data gradient), conv weight gradient, norm backward,
+# losses (csrc/gemm_tc.cu t2h_conv_wgrad, csrc/gan.cu)
+# ----------------------------------------------------------------------------
+def tap_conv(a, w, bias, taps, *, n, out_hw, out=None, d_strides=None, planes_out=False, nchw_out=False, act=ACT_NONE,
+             residual=None, want_stats=False, alpha=1.0, tap_w=None):
+    """out[img, h, w, :] = act(alpha * sum_i W[tap_w[i]] . a[img + off_i, h + dy_i, w + dx_i, :] + bias) over an
+    (out_hw) output domain that may differ from a's spatial extent (reads outside a are zero).
+    a: planes whose last three dims are (h, w, C) and whose dims between the plane dim and those flatten to the
+    image index ([T,N,h,w,C] or the 4-phase [T,4,N,h,w,C]); w: planes [T, slots, Cout, C] (possibly a tap-sliced
+    view); taps: ((dy, dx, img_off), ...).  Serves every conv of the training step that the fixed-shape wrappers
+    above do not: the Discriminator's 4x4 convs (vqgan_arch.py:1160-1197), all data gradients (forward kernel on
+    the transposed weights with negated taps), the parity launches of the strided convs' data gradients."""
+    _need_cuda(a, w)
+    T = a.shape[0]
+    aH, aW, Cc = a.shape[-3:]
+    a_imgs = a.numel() // (aH * aW * Cc)
+    H, W = out_hw
+    Cout = w.shape[2]
+    assert w.shape[3] == Cc and w.stride(3) == 1 and w.stride(2) == Cc, (a.shape, w.shape)
+    b_term_g = (w.stride(0) // w.stride(1)) if w.shape[0] > 1 else max(w.shape[1], max(tap_w or (0,)) + 1)
+    slots = w.shape[1] if tap_w is None else max(tap_w) + 1
+    stats, cpg = _stats_for(Cout, n, a.device, want_stats and not planes_out and not nchw_out and out is None)
+    if out is None:
+        if nchw_out:
+            out = torch.empty((n, Cout, H, W), dtype=torch.float32, device=a.device)
+            d_strides = (Cout * H * W, W, 1, H * W)
+        else:
+            out = _alloc_out((n, H, W, Cout), planes_out, T, a.device)
+            d_strides = (H * W * Cout, W * Cout, Cout, 1)
+    _tapgemm(a=a, a_term_imgs=a_imgs // T, a_imgs=a_imgs, a_bcast=0, n_img=n, H=H, W=W, a_H=aH, a_W=aW, Cc=Cc,
+             a_sw=Cc, a_sh=aW * Cc, a_sn=aH * aW * Cc,
+             b=w, b_term_g=b_term_g, b_groups=(w.shape[0] - 1) * b_term_g + slots, b_batched=0, n_out=Cout, b_sn=Cc,
+             b_sg=w.stride(1),
+             taps=taps, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
+             d_plane=n * H * W * Cout, bias=bias, bias_mode=BIAS_COL, act=act, residual=residual, alpha=alpha,
+             gn_stats=stats, gn_cpg=cpg, tap_w=tap_w)
+    if want_stats:
+        return out, stats
+    return out
+
+
+def conv_wgrad(dy, x, taps, dw, *, n, alpha=1.0, k_split=0):
+    """dw[tap, co, ci] += alpha * sum_{img,h,w} dy[img,h,w,co] * x[img + off, h + dy_t, w + dx_t, ci].
+    dy: planes [T,N,H,W,Co]; x: planes [T,(phases,)N,h,w,Ci] (the forward conv's input operand, as saved);
+    dw: fp32 [ntaps, Co, Ci_ld] (rows 16-byte aligned), accumulated."""
+    _need_cuda(dy, x, dw)
+    lib = _lib.load()
+    T = dy.shape[0]
+    N, H, W, Co = dy.shape[1:]
+    xH, xW, Ci = x.shape[-3:]
+    x_imgs = x.numel() // (xH * xW * Ci)
+    assert N == n and dy.is_contiguous() and x.is_contiguous() and x.shape[0] == T
+    assert dw.dim() == 3 and dw.shape[0] == len(taps) and dw.shape[1] == Co and dw.shape[2] == Ci and dw.stride(2) == 1
+    p = _lib.ConvWgradParams()
+    p.dy = dy.data_ptr(); p.dy_terms = T; p.dy_term_imgs = N; p.dy_imgs = T * N
+    p.n_img, p.H, p.W, p.cout = N, H, W, Co
+    p.dy_sw, p.dy_sh, p.dy_sn = Co, W * Co, H * W * Co
+    p.x = x.data_ptr(); p.x_terms = T; p.x_term_imgs = x_imgs // T; p.x_imgs = x_imgs
+    p.x_H, p.x_W, p.cin = xH, xW, Ci
+    p.x_sw, p.x_sh, p.x_sn = Ci, xW * Ci, xH * xW * Ci
+    p.ntaps = len(taps)
+    for i, (ty, tx, off) in enumerate(taps):
+        p.tap_dy[i], p.tap_dx[i], p.tap_img_off[i] = ty, tx, off
+    p.dw = dw.data_ptr(); p.dw_tap_stride = dw.stride(0); p.dw_ld = dw.stride(1)
+    p.alpha = alpha
+    p.nterms = 3 if T == 2 else 1
+    p.k_split = k_split
+    _count()
+    if _PROFILE["on"]:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.t2h_conv_wgrad(C.byref(p), _stream()))
+        e1.record()
+        algo = 2.0 * N * H * W * Co * Ci * len(taps)
+        _PROFILE["records"].append((algo, algo * p.nterms, e0, e1, ("wgrad", N, H, W, Co, Ci * len(taps))))
+        return dw
+    _lib.check(lib.t2h_conv_wgrad(C.byref(p), _stream()))
+    return dw
+
+
+ACT_CODE = {None: 0, "none": 0, "swish": 1, "lrelu": 2}
+
+
+def norm_apply(x, stats, gamma, beta, *, act, groups, eps, n=None, terms=None):
+    """act(norm(x)*gamma+beta) -> planes.  x fp32 [N,H,W,C]; with n=1 the whole batch is one normalisation domain
+    (BatchNorm2d in training mode: groups = C)."""
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    terms = terms or get_terms()
+    nn_, hw = (N, H * W) if n is None else (n, N * H * W // n)
+    out = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_gn_apply(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(out), nn_, hw, Cc, groups,
+                                        eps, ACT_CODE[act], terms, _stream()))
+    return out
+
+
+def norm_stats(x, groups, n=None):
+    """(sum, sumsq) [n, groups, 2] fp64 of fp32 [N,H,W,C] (n=1: over the whole batch)"""
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    nn_, hw = (N, H * W) if n is None else (n, N * H * W // n)
+    stats = torch.zeros((nn_, groups, 2), dtype=torch.float64, device=x.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_gn_stats(_ptr(x), _ptr(stats), nn_, hw, Cc, groups, _stream()))
+    return stats
+
+
+def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=None, add=None, want_planes=False,
+             n=None, terms=None):
+    """backward of act(norm(x)*gamma+beta): -> dx fp32 (+ add) [, planes of dx]; dgamma/dbeta accumulated"""
+    _need_cuda(x, dy)
+    N, H, W, Cc = x.shape
+    terms = terms or get_terms()
+    nn_, hw = (N, H * W) if n is None else (n, N * H * W // n)
+    dx = torch.empty_like(x)
+    planes = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device) if want_planes else None
+    ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
+    assert dy.is_contiguous() and x.is_contiguous() and (add is None or add.is_contiguous())
+    _count(3)
+    _lib.check(_lib.load().t2h_norm_bwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add), _ptr(dx),
+                                        _ptr(planes), terms, _ptr(dgamma), _ptr(dbeta), _ptr(ws), nn_, hw, Cc, groups,
+                                        eps, ACT_CODE[act], _stream()))
+    return (dx, planes) if want_planes else dx
+
+
+def bn_update_running(stats, running_mean, running_var, count, momentum):
+    _count(1)
+    _lib.check(_lib.load().t2h_bn_update_running(_ptr(stats), _ptr(running_mean), _ptr(running_var), count, momentum,
+                                                 running_mean.numel(), _stream()))
+
+
+def lrelu_bwd(y_planes, dy, want_planes=True, terms=None):
+    """dpre = dy * LeakyReLU'(pre) from the sign of y = LeakyReLU(pre) (planes); -> (dpre fp32, planes or None)"""
+    _need_cuda(y_planes, dy)
+    terms = terms or y_planes.shape[0]
+    dpre = torch.empty_like(dy)
+    planes = torch.empty((terms,) + tuple(dy.shape), dtype=torch.float16, device=dy.device) if want_planes else None
+    _count(1)
+    _lib.check(_lib.load().t2h_lrelu_bwd(_ptr(y_planes), _ptr(dy), _ptr(dpre), _ptr(planes), terms, dy.numel(),
+                                         _stream()))
+    return dpre, planes
+
+
+def planes_s2d(a):
+    """planes [T,N,H,W,C] -> space-to-depth planes [T,4,N,H/2,W/2,C]"""
+    _need_cuda(a)
+    T, N, H, W, Cc = a.shape
+    assert a.is_contiguous()
+    out = torch.empty((T, 4, N, H // 2, W // 2, Cc), dtype=torch.float16, device=a.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_planes_s2d(_ptr(a), _ptr(out), T, N, H, W, Cc, _stream()))
+    return out
+
+
+def sumpool2(x):
+    """adjoint of nearest x2: fp32 [N,2H,2W,C] -> [N,H,W,C]"""
+    _need_cuda(x)
+    N, H2, W2, Cc = x.shape
+    out = torch.empty((N, H2 // 2, W2 // 2, Cc), dtype=torch.float32, device=x.device)
+    _count(1)
+    _lib.check(_lib.load().t2h_sumpool2(_ptr(x), _ptr(out), N, H2 // 2, W2 // 2, Cc, _stream()))
+    return out
+
+
+def vq_bwd(z, codebook, idx, book_id, dzq, dcodebook, coef_z, coef_e):
+    """dz = dzq + coef_z (z - e); dcodebook[book, idx] += coef_e (e - z).  z fp32 [B,H,W,D] (patch size 1)"""
+    _need_cuda(z, codebook)
+    n_books, n_e, D = codebook.shape
+    assert z.shape[-1] == D and z.is_contiguous() and dcodebook.is_contiguous()
+    dz = torch.empty_like(z)
+    _count(1)
+    _lib.check(_lib.load().t2h_vq_bwd(_ptr(z), _ptr(codebook), _ptr(idx.contiguous()), _ptr(book_id), _ptr(dzq),
+                                      _ptr(dz), _ptr(dcodebook), z.numel() // D, D, n_books, n_e, coef_z, coef_e,
+                                      _stream()))
+    return dz
+
+
+def l1_loss(x, xrec, sum_out, gscale=0.0, want_grad=True):
+    """sum_out[0] += sum|x - xrec|; -> grad = gscale*sign(xrec - x) (or None)"""
+    _need_cuda(x, xrec)
+    assert x.is_contiguous() and xrec.is_contiguous() and x.shape == xrec.shape
+    grad = torch.empty_like(xrec) if want_grad else None
+    _count(1)
+    _lib.check(_lib.load().t2h_l1_loss(_ptr(x), _ptr(xrec), _ptr(grad), _ptr(sum_out), x.numel(), gscale, _stream()))
+    return grad
+
+
+def hinge_loss(logits, sum_out, sgn, gscale=0.0, want_grad=True):
+    _need_cuda(logits)
+    assert logits.is_contiguous()
+    grad = torch.empty_like(logits) if want_grad else None
+    _count(1)
+    _lib.check(_lib.load().t2h_hinge_loss(_ptr(logits), _ptr(grad), _ptr(sum_out), logits.numel(), float(sgn), gscale,
+                                          _stream()))
+    return grad
+
+
+def diffaug_fwd(x, r, t):
+    """DiffAugment 'color,translation' of fp32 NCHW [B,3,H,W]; r fp32 [B,3], t int32 [B,2]"""
+    _need_cuda(x, r, t)
+    B, Cc, H, W = x.shape
+    assert Cc == 3 and x.is_contiguous() and r.dtype == torch.float32 and t.dtype == torch.int32
+    out = torch.empty_like(x)
+    ws = torch.empty((B,), dtype=torch.float64, device=x.device)
+    _count(2)
+    _lib.check(_lib.load().t2h_diffaug_fwd(_ptr(x), _ptr(r), _ptr(t), _ptr(ws), _ptr(out), B, H, W, _stream()))
+    return out
+
+
+def diffaug_bwd(dout, r, t):
+    _need_cuda(dout, r, t)
+    B, Cc, H, W = dout.shape
+    assert Cc == 3 and dout.is_contiguous()
+    dx = torch.empty_like(dout)
+    ws = torch.empty((B,), dtype=torch.float64, device=dout.device)
+    _count(2)
+    _lib.check(_lib.load().t2h_diffaug_bwd(_ptr(dout), _ptr(r), _ptr(t), _ptr(ws), _ptr(dx), B, H, W, _stream()))
+    return dx
+
+
+def adaptive_weight(rg, gg, out, inv_scale, wmax, enable):
+    _need_cuda(rg, gg, out)
+    assert rg.numel() == gg.numel() and rg.is_contiguous() and gg.is_contiguous()
+    _count(1)
+    _lib.check(_lib.load().t2h_adaptive_weight(_ptr(rg), _ptr(gg), rg.numel(), inv_scale, wmax, enable, _ptr(out),
+                                               _stream()))
+    return out
+
+
+def axpy_dev(a, b, w):
+    """a + w[0]*b with the scalar w on the device"""
+    _need_cuda(a, b, w)
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    out = torch.empty_like(a)
+    _count(1)
+    _lib.check(_lib.load().t2h_axpy_dev(_ptr(a), _ptr(b), _ptr(w), _ptr(out), a.numel(), _stream()))
+    return out
+
+
+def sample_step(logits_own, u, tex, x_t, unmasked, *, t, temp, seed, step, n_heads, cont_stride=1024):
+    """one reveal step of the diffusion sampler, in place on x_t [M] int64 / unmasked [M] uint8"""
+    _need_cuda(logits_own, u, tex, x_t, unmasked)
+    M, ncls = logits_own.shape
+    assert logits_own.is_contiguous() and u.numel() == M and x_t.numel() == M and unmasked.dtype == torch.uint8
+    _count(1)
+    _lib.check(_lib.load().t2h_sample_step(_ptr(logits_own), _ptr(u), _ptr(tex), _ptr(x_t), _ptr(unmasked), M, ncls,
+                                           n_heads, 1.0 / float(t), 1.0 / float(temp), int(seed), int(step), cont_stride,
+                                           _stream()))
