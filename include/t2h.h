@@ -145,6 +145,8 @@ typedef struct t2h_tapgemm_params {
   int32_t use_tap_w;     /* 1: tap i reads weight slot tap_w[i] of B instead of slot i (the data gradient of a
                             strided conv uses a subset of the taps per output parity, in place)          */
   int32_t tap_w[T2H_MAX_TAPS];
+  int32_t accumulate;    /* 1: D += result (TMA reduce-add) even without split-K -- gradient accumulation over
+                            micro-batches; same requirements as k_split                                  */
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);

@@ -61,13 +61,18 @@ def transformer_logits(sd, idx, segm_tokens, texture_tokens, n_head):
 
 
 def sample_fn(logits_fn, segm_tokens, texture_mask, latent_shape, mask_id, sample_steps, temp=1.0,
-              trace=None):
+              trace=None, reveal_u=None):
     """BaseSampleModel.sample_fn (sample_model.py:256-328).
 
     logits_fn(x_t, segm_tokens, texture_tokens) -> list of 18 [B,T,1024] logits.
     Uses the global torch RNG exactly as the reference does: per step one torch.rand for the reveal
     mask, then one Categorical draw per codebook that has positions to reveal, ascending codebook order.
     If ``trace`` is a list, (x_t, changes) of every step are appended (for teacher-forced parity).
+    ``reveal_u`` [steps, B, T] replaces the per-step torch.rand draws (step index 0 = the first, t = sample_steps),
+    making the reveal schedule a pure function of its argument.
+
+    Pinned: tests/test_sample_oracle.py reproduces, token for token, the fixture that oracle/make_golden_sample.py
+    recorded from the REAL BaseSampleModel.sample_fn under the same global seed.
     """
     B = segm_tokens.shape[0]
     device = segm_tokens.device
@@ -78,7 +83,10 @@ def sample_fn(logits_fn, segm_tokens, texture_mask, latent_shape, mask_id, sampl
     tex_flat = texture_tokens.view(-1)
     out = [torch.full(tex_flat.size(), -1, dtype=torch.long, device=device) for _ in range(18)]
     for t in reversed(range(1, sample_steps + 1)):
-        changes = torch.rand(x_t.shape, device=device) < 1.0 / float(t)
+        # the reference compares against 1 / t.float() computed in fp32 (:283-286)
+        thr = 1 / torch.full((B,), t, device=device, dtype=torch.long).float().unsqueeze(-1)
+        u = torch.rand(x_t.shape, device=device) if reveal_u is None else reveal_u[sample_steps - t]
+        changes = u < thr
         changes = torch.bitwise_xor(changes, torch.bitwise_and(changes, unmasked))
         unmasked = torch.bitwise_or(unmasked, changes)
         if trace is not None:

@@ -130,3 +130,17 @@ TINY_VQGAN_TRAIN = dict(
     dec=dict(in_channels=3, resolution=64, z_channels=32, ch=32, out_ch=3, num_res_blocks=1, attn_resolutions=[8],
              ch_mult=[1, 2, 2, 4], dropout=0.0, resamp_with_conv=True, give_pre_end=False),
     n_embed=64, embed_dim=32, ndf=16, disc_layers=3, disc_start_step=0, step=5, batch=2)
+
+
+# reduced index-prediction transformer for the sample_fn fixture: the reference loop hard-codes the 32x16 token grid
+# and the 1024-per-texture index stride (sample_model.py:270,313), so those are kept; width / depth are reduced
+SAMPLE_TRANSFORMER = dict(codebook_size=18432, segm_codebook_size=32, texture_codebook_size=18, bert_n_emb=64,
+                          bert_n_layers=2, bert_n_head=4, block_size=512, latent_shape=[32, 16], embd_pdrop=0.0,
+                          resid_pdrop=0.0, attn_pdrop=0.0, num_head=18)
+SAMPLE_BATCH, SAMPLE_STEPS = 2, 12
+
+
+def sample_inputs(seed, B):
+    g = _gen(seed, "sample_inputs")
+    segm_tokens = torch.randint(0, 32, (B, 512), generator=g)
+    return segm_tokens, blocky_mask(seed, B, 512, 256, 64)

@@ -209,3 +209,59 @@ def test_config4_sampler_logits_batch4(cuda):
     own = s.sampler_fn.forward_own_logits(idx, segm, tex, dest, hf)
     want_own = got.gather(2, tex.view(B, T, 1, 1).expand(B, T, 1, 1024)).view(B * T, 1024)
     assert torch.equal(own, want_own)
+
+
+def test_config4_sample_fn_against_pinned_oracle(cuda):
+    """BASELINE config 4 sampling loop (B=4, real 24x512 transformer, 18 heads) against oracle/transformer_ref.sample_fn
+    (pinned token-for-token to the real BaseSampleModel.sample_fn by tests/test_sample_oracle.py):
+      * identical reveal schedule under shared reveal uniforms (the set revealed at every step),
+      * per-step own-head logits at the traced states equal the oracle's logits within 1e-3,
+      * every token comes from its position's own texture codebook; all positions end unmasked,
+      * CUDA-graph replay == eager launches, and a weight update invalidates the captured graph."""
+    from oracle import transformer_ref
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import Sampler
+    ops.set_precision("fp32")
+    torch.manual_seed(11)
+    s = Sampler(SAMPLER_OPT)
+    with torch.no_grad():
+        s.sampler_fn.pos_emb.normal_(0, 0.02)
+    s = s.to(cuda).eval()
+    sd = {k: v.detach() for k, v in s.sampler_fn.state_dict().items()}
+    B, T, steps = 4, 512, 8
+    g = torch.Generator().manual_seed(6)
+    segm = torch.randint(0, 1024, (B, T), generator=g).to(cuda)
+    mask = R.blocky_mask(9, B, 512, 256, 64).to(cuda)
+    u = torch.rand((steps, B, T), generator=g).to(cuda)
+    trace = []
+    out, x_t = s.sample_fn(segm, mask, sample_steps=steps, reveal_u=u, seed=77, trace=trace)
+    # oracle run with the same reveal uniforms (its own categorical draws): the reveal sets must coincide
+    otrace = []
+    with torch.no_grad():
+        transformer_ref.sample_fn(lambda x, sg, tx: transformer_ref.transformer_logits(sd, x, sg, tx, n_head=8), segm,
+                                  mask, [32, 16], 18432, steps, trace=otrace, reveal_u=u)
+    assert len(trace) == len(otrace) == steps
+    for i, ((xb, ch), (oxb, och)) in enumerate(zip(trace, otrace)):
+        assert torch.equal(ch, och), f"step {i}: revealed set differs from the reference schedule"
+    tex = torch.nn.functional.interpolate(mask, (32, 16), mode="nearest").view(B, T).long()
+    assert bool((x_t != 18432).all()) and bool(((x_t // 1024) == tex).all())
+    for k in range(18):
+        assert bool(((out[k] >= 0) == (tex == k)).all()) and int(out[k].max()) < 1024
+    # teacher-forced: the logits our loop sampled from at its own traced states vs the oracle's logits there
+    for i in (0, steps // 2, steps - 1):
+        xb = trace[i][0]
+        with torch.no_grad():
+            want = torch.stack(transformer_ref.transformer_logits(sd, xb, segm, tex, n_head=8), 2)
+        got = s.sampler_fn.forward_logits(xb, segm, tex)
+        assert _rel(got, want) < TOL, i
+    # graph replay vs eager: same random inputs -> same tokens
+    out2, x_t2 = s.sample_fn(segm, mask, sample_steps=steps, reveal_u=u, seed=77, use_graph=False)
+    assert torch.equal(x_t, x_t2)
+    # a weight change must not replay stale packed weights
+    with torch.no_grad():
+        for p in s.sampler_fn.parameters():
+            p.mul_(1.01)
+    _, xa = s.sample_fn(segm, mask, sample_steps=steps, reveal_u=u, seed=77)
+    _, xb2 = s.sample_fn(segm, mask, sample_steps=steps, reveal_u=u, seed=77, use_graph=False)
+    assert torch.equal(xa, xb2)
+    assert len(s._graphs) <= s.MAX_GRAPHS

@@ -10,7 +10,7 @@ import golden_recipes as R
 
 pytestmark = pytest.mark.gpu
 
-TOL = {2: 2e-5, 1: 4e-3}      # 3-product (fp32-equivalent) / single-product operands
+TOL = {2: 3e-5, 1: 4e-3}      # 3-product (fp32-equivalent) / single-product operands; reference = fp64 autograd
 
 
 def _rel(got, ref):
@@ -50,9 +50,11 @@ def test_conv_forward_dgrad_wgrad_match_autograd(cuda, case, terms):
     x = torch.randn(N, Ci, H, W, generator=g).to(cuda).requires_grad_(True)
     w = (torch.randn(Co, Ci, K, K, generator=g) / (Ci * K * K) ** 0.5).to(cuda).requires_grad_(True)
     b = (0.1 * torch.randn(Co, generator=g)).to(cuda).requires_grad_(True)
-    y = _torch_conv(kind, x, w, b)
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y = _torch_conv(kind, x64, w64, b64)
     dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(cuda)
-    y.backward(dy)
+    y.backward(dy.double())
+    xg, wg, y = x64.grad, w64.grad, y.detach()
     Ho, Wo = G.out_hw(kind, H, W)
     assert y.shape[2:] == (Ho, Wo)
     # ---- operands as the training step holds them
@@ -71,18 +73,18 @@ def test_conv_forward_dgrad_wgrad_match_autograd(cuda, case, terms):
     # ---- weight gradient
     gw = torch.zeros_like(m)
     G.wgrad(kind, dyp, a, gw, n=N)
-    want_gw = G.oihw_to_master(w.grad)
+    want_gw = G.oihw_to_master(wg)
     assert _rel(gw, want_gw) < TOL[terms], "wgrad"
     G.wgrad(kind, dyp, a, gw, n=N, alpha=0.5)                              # accumulates
     assert _rel(gw, 1.5 * want_gw) < TOL[terms], "wgrad accumulate"
     # ---- data gradient
     dx = G.dgrad(kind, dyp, wt, n=N, in_hw=(H, W))
     assert dx.shape == (N, H, W, G.pad8(Ci))
-    assert _rel(dx[..., :Ci].permute(0, 3, 1, 2), x.grad) < TOL[terms], "dgrad"
+    assert _rel(dx[..., :Ci].permute(0, 3, 1, 2), xg) < TOL[terms], "dgrad"
     if Ci == 3:   # image gradient written straight into NCHW
         dx_img = torch.zeros((N, 3, H, W), device=cuda)
         G.dgrad(kind, dyp, wt, n=N, in_hw=(H, W), cin=3, out=dx_img, d_strides=(3 * H * W, W, 1, H * W))
-        assert _rel(dx_img, x.grad) < TOL[terms], "dgrad nchw"
+        assert _rel(dx_img, xg) < TOL[terms], "dgrad nchw"
 
 
 @pytest.mark.parametrize("act,groups_mode", [("swish", "gn"), (None, "gn"), ("lrelu", "bn")])

@@ -40,7 +40,7 @@ class TapGemmParams(C.Structure):
         ("alpha", C.c_float),
         ("residual", C.c_void_p),
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
-        ("use_tap_w", C.c_int32), ("tap_w", C.c_int32 * MAX_TAPS),
+        ("use_tap_w", C.c_int32), ("tap_w", C.c_int32 * MAX_TAPS), ("accumulate", C.c_int32),
     ]
 
 

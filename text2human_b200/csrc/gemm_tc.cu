@@ -1020,6 +1020,12 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   }
   T2H_CHECK_ARG((long long)P.total_tiles * P.ksplit < (1LL << 31), "tapgemm: too many work items");
   P.total_work = P.total_tiles * P.ksplit;
+  if (p->accumulate) {
+    T2H_CHECK_ARG(!swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode != T2H_BIAS_ROW &&
+                      p->act == T2H_ACT_NONE && !p->gn_stats,
+                  "tapgemm: accumulate needs an aligned fp32 output and no row bias/act/residual");
+    P.accum = 1;
+  }
   // ---- CTA pairs: plain row GEMMs with at least two row tiles run as clusters of two CTAs on vertically
   // adjacent row tiles that share each weight tile through TMA multicast (-1/3 of the L2->SM operand bytes)
   P.pair = 0;

@@ -91,7 +91,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
              tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0,
-             tap_w=None):
+             tap_w=None, accumulate=False):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -122,6 +122,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.k_split = k_split
     p.bias_sn = bias_sn
     p.a_mn, p.b_mn = a_mn, b_mn
+    p.accumulate = 1 if accumulate else 0
     if tap_w is not None:
         p.use_tap_w = 1
         for i, wi in enumerate(tap_w):
@@ -327,7 +328,7 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
     return out
 
 
-def wgrad(dy, x, out, k_split=0, alpha=1.0):
+def wgrad(dy, x, out, k_split=0, alpha=1.0, accumulate=False):
     """out[n_out, n_in] += alpha * dy^T @ x over the rows (tokens).  dy planes [T,M,n_out], x planes [T,M,n_in]
     exactly as the forward / backward passes hold them (row = token): both are consumed as MN-major operands,
     so no transposed copy exists.  With ``k_split`` >= 2 the token range is split over the SMs and reduce-added
@@ -340,7 +341,7 @@ def wgrad(dy, x, out, k_split=0, alpha=1.0):
              a_sw=dy.stride(1), a_sh=dy.stride(0), a_sn=dy.stride(0),
              b=x, b_term_g=1, b_groups=T, b_batched=0, n_out=Ni, b_sn=x.stride(1), b_sg=x.stride(0),
              taps=_TAPS_1, d=out, d_mode=OUT_F32, d_strides=(0, 0, out.stride(0), 1), alpha=alpha,
-             k_split=k_split, a_mn=1, b_mn=1)
+             k_split=k_split, a_mn=1, b_mn=1, accumulate=accumulate)
     return out
 
 

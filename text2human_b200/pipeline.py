@@ -214,9 +214,14 @@ class Sampler(nn.Module):
     """The absorbing-diffusion sampling loop of BaseSampleModel (sample_model.py:256-328) around
     TransformerMultiHead, without the reference's per-codebook host synchronisations.
 
-    RNG: one ``torch.rand`` per step for the reveal schedule and one ``torch.multinomial`` per step
-    over the logits of each position's own texture head (the reference draws every head for every
-    position and keeps one).  torch's generator is used as the random source only."""
+    RNG: torch's generator supplies ONE ``torch.rand`` of all reveal uniforms [steps, B, T] before the loop (the
+    reference draws one [B, T] per step from the same kind of stream) and one integer seed; inside the loop the
+    categorical draws come from ``t2h_sample_step`` (Gumbel-max over each position's OWN texture head with
+    Philox4x32-10 keyed by (seed, step, position, class)) -- the reference draws every head for every position with
+    18 ``Categorical.sample()`` calls and keeps one.  The law of every token is the same
+    (softmax(logits/temp) of the own head); the loop body has no ATen launches."""
+
+    MAX_GRAPHS = 4
 
     def __init__(self, opt):
         super().__init__()
@@ -230,62 +235,97 @@ class Sampler(nn.Module):
         self.shape = tuple(opt['latent_shape'])
         self.mask_id = opt['codebook_size']
         self.sample_steps = opt['sample_steps']
-        self._graphs = {}
+
+    @property
+    def _graphs(self):
+        """captured graphs live ON the transformer module (next to its packed-weight cache) so that whoever
+        invalidates the packed weights (``SamplerTrainer._drop_packed_caches``) drops them too"""
+        return self.sampler_fn.__dict__.setdefault("_t2h_graphs", {})
+
+    def _weights_signature(self):
+        """a captured graph bakes in pointers to the packed fp16 weight planes: it is only valid for the exact
+        parameter storage / version it was captured with"""
+        return tuple((p.data_ptr(), p._version) for p in self.sampler_fn.parameters())
 
     def _own_logits_fn(self, B, T, device, use_graph, rows_per_head):
         """the transformer forward for fixed (B, T, rows_per_head), returning each position's own-head logits:
         ~220 small launches per step are CPU-launch-bound, so they are captured once into a CUDA graph and
-        replayed every diffusion step"""
+        replayed every diffusion step.  -> (fn, hf, static inputs or None)"""
         m = self.sampler_fn
         Tt = ops.get_terms()
-        key = (B, T, str(device), Tt, ops.SPLIT_K["inference"], rows_per_head, use_graph)
-        hit = self._graphs.get(key)
+        key = (B, T, str(device), Tt, ops.SPLIT_K["inference"], rows_per_head, use_graph, self._weights_signature())
+        graphs = self._graphs
+        hit = graphs.get(key)
         if hit is None:
+            while len(graphs) >= self.MAX_GRAPHS:   # bounded: each entry pins a private pool of all activations
+                graphs.pop(next(iter(graphs)))
             # rows no position maps to stay zero for the lifetime of the buffer
             hf = torch.zeros((Tt, m.num_head * rows_per_head, m.n_embd), dtype=torch.float16, device=device)
 
             def fn(x_t, segm, tex, dest):
                 return m.forward_own_logits(x_t, segm, tex, dest, hf)
+            static = None
             if use_graph:
                 ex = (torch.full((B, T), self.mask_id, dtype=torch.long, device=device),
                       torch.zeros((B, T), dtype=torch.long, device=device),
                       torch.zeros((B, T), dtype=torch.long, device=device),
                       torch.arange(B * T, dtype=torch.long, device=device))
                 fn = GraphedStep(fn, ex)
-            hit = (fn, hf)
-            self._graphs[key] = hit
+                static = fn.static_in
+            hit = (fn, hf, static)
+            graphs[key] = hit
+        else:
+            graphs[key] = graphs.pop(key)           # most recently used last
         return hit
 
     @torch.no_grad()
-    def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None, use_graph=True):
+    def sample_fn(self, segm_tokens, texture_mask, temp=1.0, sample_steps=None, generator=None, use_graph=True,
+                  reveal_u=None, seed=None, trace=None):
         """segm_tokens int64 [B, T]; texture_mask float [B,1,H,W] of ids 0..17.
-        Returns (list of 18 int64 [B,T] per-codebook index maps with -1 elsewhere, final x_t)."""
+        Returns (list of 18 int64 [B,T] per-codebook index maps with -1 elsewhere, final x_t).
+        ``reveal_u`` [steps, B, T] / ``seed``: the random inputs, drawn from ``generator`` when not given.
+        ``trace``: a list that receives (x_t before the step, positions revealed in the step) per step."""
         m = self.sampler_fn
         B = segm_tokens.shape[0]
         T = int(np.prod(self.shape))
         dev = segm_tokens.device
         steps = sample_steps or self.sample_steps
         tex = ops.mask_to_ids(texture_mask, self.shape[0], self.shape[1]).view(B, T).long()
-        x_t = torch.full((B, T), self.mask_id, dtype=torch.long, device=dev)
-        unmasked = torch.zeros((B, T), dtype=torch.bool, device=dev)
-        nh, ncls = m.num_head, m.head_class_num
+        nh = m.num_head
         tex_c = tex.clamp(0, nh - 1)
         valid_tex = (tex >= 0) & (tex < nh)
+        if reveal_u is None:
+            reveal_u = torch.rand((steps, B, T), device=dev, generator=generator)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,), device=dev, generator=generator).item())
         # positions grouped by texture once per run: every step's head GEMM then only computes each position's
         # own head (the reference computes all 18 heads for every position and keeps one)
         dest, rows_per_head = m.group_by_texture(tex_c, nh)
-        logits_fn, hf = self._own_logits_fn(B, T, dev, use_graph, rows_per_head)
-        hf.zero_()  # padding rows of a previous run's grouping must not leak in (they only cost time, but keep it clean)
-        for t in range(steps, 0, -1):
-            changes = torch.rand((B, T), device=dev, generator=generator) < (1.0 / t)
-            changes = changes & ~unmasked
-            unmasked = unmasked | changes
-            own = logits_fn(x_t, segm_tokens, tex_c, dest)  # [B*T, ncls]: each position's own texture head
-            probs = torch.softmax(own / temp, dim=-1)
-            draw = torch.multinomial(probs, 1, True, generator=generator).view(B, T)
-            upd = changes & valid_tex
-            x_t = torch.where(upd, draw + 1024 * tex_c, x_t)
-        final = torch.where(unmasked & valid_tex, x_t - 1024 * tex_c, torch.full_like(x_t, -1))
+        logits_fn, hf, static = self._own_logits_fn(B, T, dev, use_graph, rows_per_head)
+        hf.zero_()  # padding rows of a previous run's grouping must not leak in
+        if static is not None:   # run the loop directly on the graph's input buffers: no per-step copies
+            x_t, segm_s, tex_s, dest_s = static
+            x_t.fill_(self.mask_id)
+            segm_s.copy_(segm_tokens)
+            tex_s.copy_(tex_c)
+            dest_s.copy_(dest)
+        else:
+            x_t = torch.full((B, T), self.mask_id, dtype=torch.long, device=dev)
+            segm_s, tex_s, dest_s = segm_tokens, tex_c, dest
+        unmasked = torch.zeros((B * T,), dtype=torch.uint8, device=dev)
+        tex_flat = tex.reshape(-1).contiguous()
+        reveal_u = reveal_u.contiguous()
+        for i, t in enumerate(range(steps, 0, -1)):
+            own = logits_fn(x_t, segm_s, tex_s, dest_s)   # [B*T, ncls]: each position's own texture head
+            if trace is not None:
+                before, x_before = unmasked.clone(), x_t.clone()
+            ops.sample_step(own, reveal_u[i].view(-1), tex_flat, x_t.view(-1), unmasked, t=t, temp=temp, seed=seed,
+                            step=i, n_heads=nh)
+            if trace is not None:
+                trace.append((x_before, (unmasked != before).view(B, T)))
+        x_t = x_t.clone()
+        um = unmasked.view(B, T).bool()
+        final = torch.where(um & valid_tex, x_t - 1024 * tex_c, torch.full_like(x_t, -1))
         out = [torch.where(tex == k, final, torch.full_like(final, -1)) for k in range(nh)]
         return out, x_t
 

@@ -98,7 +98,7 @@ class Block(nn.Module):
                                         sampler)
         self.mlp = nn.Sequential(
             nn.Linear(bert_n_emb, 4 * bert_n_emb),
-            nn.GELU(),  # nice
+            nn.GELU(),
             nn.Linear(4 * bert_n_emb, bert_n_emb),
             nn.Dropout(resid_pdrop),
         )
@@ -198,7 +198,10 @@ class TransformerMultiHead(nn.Module):
         ``rows_per_head`` costs one device->host read."""
         flat = texture_tokens.reshape(-1).clamp(0, num_head - 1)
         counts = torch.bincount(flat, minlength=num_head)
-        rows = max(128, (int(counts.max().item()) + 127) // 128 * 128)
+        need = max(128, int(counts.max().item()))
+        rows = 128
+        while rows < need:      # powers of two: a handful of distinct sizes (and captured graphs) for any mask
+            rows *= 2
         order = torch.argsort(flat, stable=True)
         start = torch.cumsum(counts, 0) - counts
         rank = torch.arange(flat.numel(), device=flat.device) - start[flat[order]]

@@ -80,6 +80,16 @@ class SamplerTrainer:
                 p.grad = gv
                 self.gview[id(p)] = gv
         self.n_layers = len(m.blocks)
+        self.sync_from_rank0()
+
+    def sync_from_rank0(self):
+        """Replicas must start (and resume) from identical parameters and optimiser state -- torch DDP broadcasts
+        them at construction; call this again after loading a checkpoint on one rank.  The random draws
+        (``q_sample`` masks, diffusion times) should differ per rank: pass each rank its own ``generator``."""
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            for t in (self.flat_p, self.flat_m, self.flat_v):
+                dist.broadcast(t, 0)
+            self._drop_packed_caches()
 
     def g(self, p):
         return self.gview[id(p)]
@@ -110,6 +120,7 @@ class SamplerTrainer:
         # Adam kernel does not bump
         for mod in self.m.modules():
             mod.__dict__.pop("_t2h_cache", None)
+            mod.__dict__.pop("_t2h_graphs", None)   # captured sampler graphs bake in the packed-weight pointers
 
     # ------------------------------------------------------------------ diffusion bookkeeping (torch RNG)
     def q_sample(self, x_0, t, generator=None):

@@ -322,10 +322,13 @@ class Encoder(nn.Module):
         h = self._body(_conv_in_nchw(self.conv_in, x_nchw))
         return _conv_out(self.norm_out, self.conv_out, h, nchw=False)
 
-    @torch.no_grad()
     def forward(self, x):
-        h = self._body(_conv_in_nchw(self.conv_in, x))
-        return _conv_out(self.norm_out, self.conv_out, h, nchw=True)
+        from . import vqgan_autograd as VA
+        if VA.recording(self, x):       # training: one autograd node with the hand-written backward
+            return VA.encoder_forward(self, x)
+        with torch.no_grad():
+            h = self._body(_conv_in_nchw(self.conv_in, x))
+            return _conv_out(self.norm_out, self.conv_out, h, nchw=True)
 
 
 class Decoder(nn.Module):
@@ -410,12 +413,15 @@ class Decoder(nn.Module):
         h = self._trunk(_conv_in_nhwc(self.conv_in, z), bot_h=bot_h)
         return self._finish(h, nchw_out)
 
-    @torch.no_grad()
     def forward(self, z, bot_h=None):
         self.last_z_shape = z.shape
-        bh = ops.nchw_to_nhwc(bot_h) if bot_h is not None else None
-        h = self._trunk(_conv_in_nchw(self.conv_in, z), bot_h=bh)
-        return self._finish(h, True)
+        from . import vqgan_autograd as VA
+        if VA.recording(self, z, bot_h):   # training: trunk node + (norm_out, conv_out) node
+            return VA.decoder_forward(self, z, bot_h)
+        with torch.no_grad():
+            bh = ops.nchw_to_nhwc(bot_h) if bot_h is not None else None
+            h = self._trunk(_conv_in_nchw(self.conv_in, z), bot_h=bh)
+            return self._finish(h, True)
 
     @torch.no_grad()
     def get_feature_top(self, z):
@@ -472,6 +478,36 @@ class DecoderRes(nn.Module):
     def forward(self, z):
         self.last_z_shape = z.shape
         return ops.nhwc_to_nchw(self._trunk(_conv_in_nchw(self.conv_in, z)))
+
+
+# ----------------------------------------------------------------------------
+# Patch discriminator (reference :1154-1203)
+# ----------------------------------------------------------------------------
+class Discriminator(nn.Module):
+    """conv4x4 s2 + LeakyReLU(0.2) | (n_layers-1) x [conv4x4 s2, BatchNorm, LeakyReLU] | [conv4x4 s1, BatchNorm,
+    LeakyReLU] | conv4x4 s1 -> 1 channel.  The nn.Sequential ``main`` only holds the parameters / BatchNorm buffers
+    under the reference's state_dict keys; the arithmetic runs in libt2h (``vqgan_train.DiscNet``): 16-tap tcgen05
+    convs on space-to-depth planes, BatchNorm as one-image GroupNorm(groups=C) kernels with the LeakyReLU fused."""
+
+    def __init__(self, nc, ndf, n_layers=3):
+        super().__init__()
+        layers = [nn.Conv2d(nc, ndf, kernel_size=4, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        ndf_mult = 1
+        for n in range(1, n_layers):
+            ndf_mult_prev, ndf_mult = ndf_mult, min(2**n, 8)
+            layers += [nn.Conv2d(ndf * ndf_mult_prev, ndf * ndf_mult, kernel_size=4, stride=2, padding=1, bias=False),
+                       nn.BatchNorm2d(ndf * ndf_mult), nn.LeakyReLU(0.2, True)]
+        ndf_mult_prev, ndf_mult = ndf_mult, min(2**n_layers, 8)
+        layers += [nn.Conv2d(ndf * ndf_mult_prev, ndf * ndf_mult, kernel_size=4, stride=1, padding=1, bias=False),
+                   nn.BatchNorm2d(ndf * ndf_mult), nn.LeakyReLU(0.2, True)]
+        layers += [nn.Conv2d(ndf * ndf_mult, 1, kernel_size=4, stride=1, padding=1)]
+        self.main = nn.Sequential(*layers)
+
+    def forward(self, x):
+        """fp32 NCHW [N,3,H,W] -> patch logits fp32 [N,1,h,w].  With autograd enabled the call is recorded as ONE
+        autograd node whose backward is the hand-written discriminator backward (``vqgan_autograd``)."""
+        from . import vqgan_autograd as VA
+        return VA.discriminator_forward(self, x)
 
 
 # ----------------------------------------------------------------------------
@@ -584,11 +620,14 @@ class VectorQuantizerTexture(_TextureQuantizerBase):
         r["ids"] = ids
         return r
 
-    @torch.no_grad()
     def forward(self, z, segm_map, temp=None, rescale_logits=False, return_logits=False):
         _check_gumbel_args(temp, rescale_logits, return_logits)
-        r = self.forward_nhwc(ops.nchw_to_nhwc(z), segm_map, want_nchw=True)
-        return r["zq_nchw"], r["loss"], (None, r["idx_cont"], list(r["idx_list"].unbind(0)))
+        from . import vqgan_autograd as VA
+        if VA.recording(self, z):          # training: straight-through + codebook-loss gradients
+            return VA.quantizer_texture_forward(self, z, segm_map)
+        with torch.no_grad():
+            r = self.forward_nhwc(ops.nchw_to_nhwc(z), segm_map, want_nchw=True)
+            return r["zq_nchw"], r["loss"], (None, r["idx_cont"], list(r["idx_list"].unbind(0)))
 
     @torch.no_grad()
     def get_codebook_entry(self, indices_list, segm_map, shape, nhwc=False):
