@@ -264,6 +264,83 @@ def train_workload(dev, precision, world, batch=16, steps=4):
                 if world > 1 else "none (1 GPU)", params=tr.flat_p.numel())
 
 
+def vqgan_train_workload(dev, precision, rank, world, global_batch=64, micro=8, steps=2):
+    """BASELINE config 5: the VQGAN GAN training step (vqgan_model.py:444-488 + :329-344:
+    generator forward, L1, DiffAugment, discriminator, adaptive weight, backward, discriminator update, two Adams),
+    global batch 64 split over the ranks (strong scaling, as train_vqvae.py under DDP), gradients all-reduced over
+    NCCL in buckets that are launched as the backward pass finishes them.  Every rank must call this (collectives
+    inside).  Precision: single-product fp16 operands with fp32 accumulation / master weights / Adam -- the
+    analogue of config 5's "bf16 autocast" (one tensor-core product per contraction); LPIPS stubbed to zero.
+    Also times the same step with the all-reduce disabled: the difference is the EXPOSED (non-overlapped)
+    communication time."""
+    import contextlib
+    import golden_recipes as R
+    import torch.distributed as dist
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+    from text2human_b200.vqgan_arch import Discriminator
+    from text2human_b200.vqgan_train import VQGANTrainer
+    old_terms = ops.get_terms()
+    ops.set_precision(precision)
+    try:
+        per_gpu = global_batch // world
+        mb = min(micro, per_gpu)
+        torch.manual_seed(5)
+        with contextlib.redirect_stdout(sys.stderr):
+            model = VQImageSegmTextureModel(VQVAE_TOP).to(dev)
+        disc = Discriminator(3, 64, n_layers=3).to(dev)
+        cb = R.codebooks(7, 18, 1024, 256, "trained")
+        with torch.no_grad():
+            for k, e in enumerate(model.quantize.embedding_list):
+                e.weight.copy_(cb[k])
+        tr = VQGANTrainer(model, disc, lr=1e-4, disc_start_step=0, micro_batch=mb)
+        data = dict(image=R.image(300 + rank, per_gpu, 3, 512, 256).to(dev),
+                    texture_mask=R.blocky_mask(300 + rank, per_gpu, 512, 256, 32).to(dev))
+        gen = torch.Generator(device=dev).manual_seed(17 + rank)     # per-rank DiffAugment draws
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(n, reduce_on):
+            tr.force_no_reduce = not reduce_on
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ops.COUNTERS["launches"]
+            e0.record()
+            for i in range(n):
+                tr.optimize_parameters(data, 2 + i, gen)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            return ms, (ops.COUNTERS["launches"] - l0) // n
+        timed(1, True)                                   # warm-up (kernel configuration, allocator)
+        ms, launches = timed(steps, True)
+        ms_nr = timed(steps, False)[0] if world > 1 else ms
+        tr.force_no_reduce = False
+        loss = tr.losses()
+        gflop_img = 3 * GFLOP_PER_IMG                    # generator forward + data + weight gradients (2*MAC)
+        return dict(global_batch=global_batch, per_gpu_batch=per_gpu, micro_batch=mb, n_gpus=world, scaling="strong",
+                    ms_per_step=ms, img_per_s=global_batch / (ms / 1e3), launches_per_step=launches,
+                    ms_per_step_without_allreduce=ms_nr, exposed_allreduce_ms=max(0.0, ms - ms_nr),
+                    allreduce_bytes=4 * (tr.gen.total + tr.dsc.total),
+                    buckets=dict(generator=[4 * (b - a) for a, b in tr.gen.buckets],
+                                 discriminator=[4 * (b - a) for a, b in tr.dsc.buckets],
+                                 limiting="the last generator bucket (encoder head): it closes with the final "
+                                          "backward kernel, so its reduction cannot overlap anything"),
+                    algorithmic_tflops=global_batch * gflop_img / ms, precision=precision,
+                    frac_of_peak=global_batch * gflop_img / ms / (peaks()["tf_sustained"] * world),
+                    losses={k: float(v) for k, v in loss.items()},
+                    note="LPIPS stubbed (config 5); BatchNorm / adaptive weight per micro-batch = per DDP rank")
+    finally:
+        ops._PRECISION["terms"] = old_terms
+
+
 def _reference_forward_fn(device, threads=None):
     """-> (fn(x, mask) running the reference's own VQImageSegmTextureModel.forward_step, kind): the UNMODIFIED
     reference sources staged in oracle/_ref (kind "reference"), else the oracle port (kind "port")."""
@@ -429,6 +506,12 @@ def run():
                     help="N>1 only: also time the sampler training step with its NCCL gradient all-reduce")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the short config-3 (hierarchy) and config-4 (sampler) side measurements")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="run the batch as this many concurrent slices on separate CUDA streams")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 DDP training-step measurement")
+    ap.add_argument("--train-precision", default="fp16", choices=["fp32", "fp16"],
+                    help="operand precision of the training step (fp16 = one tensor-core product, config 5's bf16 "
+                         "autocast analogue; fp32 = the 3-product parity mode)")
     ap.add_argument("--graph", action="store_true",
                     help="replay one captured CUDA graph per step (measured: no gain for this GPU-bound step)")
     args = ap.parse_args()
@@ -480,7 +563,7 @@ def run():
 
     # One step = one forward_step (~340 asynchronous launches; --graph replays them as one CUDA graph).
     def raw_step(x, m):
-        dec, loss = model.forward_step(x, m)
+        dec, loss = model.forward_step(x, m, streams=args.streams)
         return dec, loss
     step = GraphedStep(raw_step, (xs_d[0], ms_d[0])) if args.graph else raw_step
 
@@ -575,6 +658,14 @@ def run():
             for k in ("config4_fp32", "config4_tf32"):
                 if k in eager:
                     eager[k]["ours_ms_per_step"] = extra["config4_sampler"]["ms_per_diffusion_step"]
+    # ---------------- BASELINE config 5: the DDP training step (every rank takes part, every N) ----------------
+    ddp_train = None
+    if not args.no_train:
+        try:
+            ddp_train = vqgan_train_workload(dev, args.train_precision, rank, world)
+        except Exception as exc:   # a failure here must not take the headline line down (symmetric on all ranks)
+            ddp_train = dict(error=repr(exc))
+        torch.cuda.empty_cache()
     if world > 1 and args.extra_train_ddp:  # opt-in: a collective runs inside (every rank takes part)
         tw = train_workload(dev, args.precision, world)
         extra = dict(sampler_train_step=tw) if rank == 0 else None
@@ -604,7 +695,8 @@ def run():
                     clocks=clk,
                     e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager, extra=extra,
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager,
+                    ddp_train=ddp_train, extra=extra,
                     pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
                     pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
     if world > 1:

@@ -147,6 +147,11 @@ typedef struct t2h_tapgemm_params {
   int32_t tap_w[T2H_MAX_TAPS];
   int32_t accumulate;    /* 1: D += result (TMA reduce-add) even without split-K -- gradient accumulation over
                             micro-batches; same requirements as k_split                                  */
+  int32_t k_partials;    /* >= 2: deterministic split-K: the contraction of every output tile is split over up to
+                            k_partials CTAs, slice s (s < ceil(kchunks / ceil(kchunks / k_partials)), kchunks =
+                            ceil(C / 64)) STORES alpha*A.B to d + s*d_slab; t2h_splitk_reduce_ln sums the slabs in
+                            a fixed order.  Single-image row GEMMs, no bias / act / residual                 */
+  int64_t d_slab;        /* element distance between the k_partials slabs                                  */
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
@@ -275,6 +280,14 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
  * groups the positions by texture so that each position only meets its own head, transformer_arch.py:268-273) */
 int t2h_layernorm_scatter(const float* x, const float* gamma, const float* beta, void* out, int64_t rows, int c,
                           float eps, int terms, const int64_t* row_map, int64_t out_rows, t2h_stream_t stream);
+
+/* x_out[m,:] = residual[m,:] + bias + sum_{s<n_slabs} partials[s][m,:] (slabs summed in index order: bit-reproducible),
+ * then optionally LayerNorm(x_out[m,:]) -> fp16 planes, row m written to row row_map[m] (or m) of a planes buffer of
+ * ln_rows rows.  Completes a k_partials GEMM and fuses the residual add (x = x + proj(y), x = x + mlp(.),
+ * transformer_arch.py:97-99) with the next LayerNorm (:80-81, :231).  residual may alias x_out. */
+int t2h_splitk_reduce_ln(const float* partials, int n_slabs, int64_t slab, const float* bias, const float* residual,
+                         float* x_out, const float* gamma, const float* beta, float eps, void* ln_out, int terms,
+                         const int64_t* row_map, int64_t ln_rows, int64_t rows, int c, t2h_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Training step of the index-prediction transformer

@@ -41,6 +41,7 @@ class TapGemmParams(C.Structure):
         ("residual", C.c_void_p),
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
         ("use_tap_w", C.c_int32), ("tap_w", C.c_int32 * MAX_TAPS), ("accumulate", C.c_int32),
+        ("k_partials", C.c_int32), ("d_slab", C.c_int64),
     ]
 
 
@@ -85,6 +86,7 @@ SIGNATURES = {
     "t2h_embed_sum": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "t2h_layernorm": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P]),
     "t2h_layernorm_scatter": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P, _L, _P]),
+    "t2h_splitk_reduce_ln": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _F, _P, _I, _P, _L, _L, _I, _P]),
     "t2h_pack_u8": (_I, [_P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "t2h_argmax_heads": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_f32_to_planes_t": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),

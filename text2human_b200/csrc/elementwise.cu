@@ -375,6 +375,62 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// Deterministic split-K completion fused with the residual add and the following LayerNorm: one warp per row.
+//   x_out = residual + bias + sum_s partials[s]  (s ascending);  ln_out[row_map[row]] = LN(x_out) as fp16 planes
+template <int PER_LANE>
+__global__ void splitk_reduce_ln_kernel(const float* __restrict__ part, int n_slabs, long long slab,
+                                        const float* __restrict__ bias, const float* residual, float* x_out,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        __half* __restrict__ ln_out, int terms, long long plane,
+                                        const long long* __restrict__ row_map, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warps = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float v[PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    float a = 0.f;
+    if (c < C) {
+      a = residual ? residual[row * C + c] : 0.f;
+      if (bias) a += bias[c];
+      for (int s = 0; s < n_slabs; ++s) a += part[(long long)s * slab + row * C + c];
+      x_out[row * C + c] = a;
+    }
+    v[i] = a;
+    sum += a;
+  }
+  if (!ln_out) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    const float d = c < C ? v[i] - mean : 0.f;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  const long long orow = row_map ? row_map[row] : row;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      __half hi, lo;
+      split_f16((v[i] - mean) * rstd * gamma[c] + beta[c], hi, lo);
+      ln_out[orow * C + c] = hi;
+      if (terms == 2) ln_out[plane + orow * C + c] = lo;
+    }
+  }
+}
+
 // x[b,t,:] = tok[idx] + pos[t] + segm[sg] + tex[tx]
 __global__ void embed_sum_kernel(const long long* __restrict__ idx, const long long* __restrict__ segm,
                                  const long long* __restrict__ tex, const float* __restrict__ tok_emb,
@@ -627,6 +683,27 @@ int t2h_layernorm(const float* x, const float* gamma, const float* beta, void* o
     T2H_CUDA(launch_pdl(layernorm_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, x, gamma, beta, o, rows, c, eps, terms, plane,
                         static_cast<const long long*>(nullptr)));
   T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_splitk_reduce_ln(const float* partials, int n_slabs, int64_t slab, const float* bias, const float* residual,
+                         float* x_out, const float* gamma, const float* beta, float eps, void* ln_out, int terms,
+                         const int64_t* row_map, int64_t ln_rows, int64_t rows, int c, t2h_stream_t stream) {
+  T2H_CHECK_ARG(partials && x_out && n_slabs >= 1 && rows > 0 && c > 0 && c <= 1024, "splitk_reduce_ln: bad args");
+  T2H_CHECK_ARG(!ln_out || (gamma && beta && (terms == 1 || terms == 2) && ln_rows >= (row_map ? 1 : rows)),
+                "splitk_reduce_ln: LayerNorm output needs gamma/beta/terms");
+  const int warps = 4;
+  const int grid = (int)ceil_div64(rows, warps);
+  __half* o = reinterpret_cast<__half*>(ln_out);
+  const long long plane = (long long)ln_rows * c;
+  const long long* rm = reinterpret_cast<const long long*>(row_map);
+  cudaStream_t st = as_stream(stream);
+  if (c <= 512)
+    T2H_CUDA(launch_pdl(splitk_reduce_ln_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, partials, n_slabs,
+                        (long long)slab, bias, residual, x_out, gamma, beta, eps, o, terms, plane, rm, (long long)rows, c));
+  else
+    T2H_CUDA(launch_pdl(splitk_reduce_ln_kernel<32>, dim3(grid), dim3(warps * 32), 0, st, 1, partials, n_slabs,
+                        (long long)slab, bias, residual, x_out, gamma, beta, eps, o, terms, plane, rm, (long long)rows, c));
   return T2H_OK;
 }
 

@@ -60,6 +60,7 @@ struct TapGemmDev {
   // images, both operands are NHWC planes read MN-major, the output "image" index is the tap whose (dy, dx,
   // img_off) shifts the X patch; accum: the epilogue reduce-adds into D even without split-K
   int wg, accum;
+  int partials;  // split-K without reduction: k-slice s of a tile is stored to image slot t.img + s of D
   int wg_PW, wg_PH, wg_pw, wg_ppi;
   int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
 };
@@ -540,7 +541,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           named_bar_sync(2, 128);  // staging tile complete; residual tile fully consumed
           if (elected) {
-            if (P.ksplit > 1 || P.accum)
+            if (P.partials)  // deterministic split-K: every k-slice owns a slab; a fixed-order pass sums them
+              tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img + work / P.total_tiles);
+            else if (P.ksplit > 1 || P.accum)
               tma_reduce_add_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);  // partial sum of a k-slice
             else
               tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);
@@ -1010,7 +1013,16 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   // ---- split-K: k-slices of one tile go to different CTAs and are reduce-added into a zeroed output
   P.ksplit = 1;
   P.kper = P.kchunks;
-  if (p->k_split > 1 && !swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode != T2H_BIAS_ROW &&
+  if (p->k_partials > 1) {
+    T2H_CHECK_ARG(!swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode == T2H_BIAS_NONE &&
+                      p->act == T2H_ACT_NONE && !p->gn_stats && p->n_img == 1 && p->k_split <= 1 &&
+                      p->d_slab > 0 && p->d_slab % 4 == 0,
+                  "tapgemm: k_partials needs a plain single-image fp32 GEMM output and an aligned slab stride");
+    int ks = p->k_partials < P.kchunks ? p->k_partials : P.kchunks;
+    P.kper = ceil_div(P.kchunks, ks);
+    P.ksplit = ceil_div(P.kchunks, P.kper);
+    P.partials = 1;
+  } else if (p->k_split > 1 && !swap && P.epi_mode == EPI_TMA_F32 && !p->residual && p->bias_mode != T2H_BIAS_ROW &&
       p->act == T2H_ACT_NONE && !p->gn_stats) {
     int ks = p->k_split < P.kchunks ? p->k_split : P.kchunks;
     P.kper = ceil_div(P.kchunks, ks);
@@ -1083,6 +1095,10 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     const uint64_t sh = (p->H > 1) ? (uint64_t)p->d_sh : sw * (uint64_t)p->W;
     uint64_t sn = (p->n_img > 1) ? (uint64_t)p->d_sn : sh * (uint64_t)p->H;
     uint64_t imgs = (uint64_t)p->n_img;
+    if (P.partials) {  // one slab per k-slice, addressed through the image dim
+      sn = (uint64_t)p->d_slab;
+      imgs = (uint64_t)P.ksplit;
+    }
     if (P.epi_mode == EPI_TMA_PLANES && p->d_terms == 2) {
       if (p->n_img == 1) sn = (uint64_t)p->d_plane;
       P.d_term_imgs = (int)(p->d_plane / (long long)sn);

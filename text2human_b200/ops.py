@@ -91,7 +91,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
              tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0,
-             tap_w=None, accumulate=False):
+             tap_w=None, accumulate=False, k_partials=0, d_slab=0):
     lib = _lib.load()
     T = a.shape[0]
     Tb = b.shape[0]
@@ -123,6 +123,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.bias_sn = bias_sn
     p.a_mn, p.b_mn = a_mn, b_mn
     p.accumulate = 1 if accumulate else 0
+    p.k_partials, p.d_slab = k_partials, d_slab
     if tap_w is not None:
         p.use_tap_w = 1
         for i, wi in enumerate(tap_w):
@@ -276,12 +277,16 @@ def conv3x3_s2(a_ph, w, bias, *, want_stats=False):
 # Split-K GEMMs reduce their k-slices with fp32 atomics (TMA reduce-add), so their results depend on the
 # arrival order at rounding level (~1e-7 relative).  Weight gradients use it by default (as cuDNN's wgrad
 # does); inference stays bit-reproducible run to run unless the caller opts in.
-SPLIT_K = {"wgrad": True, "inference": False}
+SPLIT_K = {"wgrad": True, "inference": False, "small_batch": True}
 
 
-def set_split_k(wgrad=None, inference=None):
-    """enable / disable the (order-non-deterministic) split-K paths; returns the previous settings"""
+def set_split_k(wgrad=None, inference=None, small_batch=None):
+    """enable / disable the split-K paths; returns the previous settings.  ``wgrad`` / ``inference`` are the
+    reduce-add (arrival-order) forms; ``small_batch`` is the deterministic stored-partials form the transformer
+    uses when a projection has too few output tiles to fill the GPU."""
     old = dict(SPLIT_K)
+    if small_batch is not None:
+        SPLIT_K["small_batch"] = bool(small_batch)
     if wgrad is not None:
         SPLIT_K["wgrad"] = bool(wgrad)
     if inference is not None:
@@ -326,6 +331,50 @@ def linear(a, w, bias=None, *, residual=None, planes_out=False, act=ACT_NONE, al
              bias=bias, bias_mode=BIAS_COL, act=act, alpha=alpha, residual=residual, k_split=k_split,
              b_mn=1 if w_kn else 0)
     return out
+
+
+def split_slices(K, k_partials):
+    """number of k-slices t2h_tapgemm actually produces for a contraction of length K and a k_partials request"""
+    kchunks = (K + 63) // 64
+    ks = min(k_partials, kchunks)
+    kper = (kchunks + ks - 1) // ks
+    return (kchunks + kper - 1) // kper
+
+
+def linear_partials(a, w, k_partials, alpha=1.0):
+    """Deterministic split-K: the k-slices of a @ w^T are STORED to separate slabs -> fp32 [S, M, Nout]
+    (S = split_slices(K, k_partials)); ``splitk_reduce_ln`` sums them in a fixed order."""
+    _need_cuda(a, w)
+    T, M, K = a.shape
+    Nout = w.shape[2]
+    assert w.shape[3] == K and a.stride(2) == 1
+    S = split_slices(K, k_partials)
+    out = torch.empty((S, M, Nout), dtype=torch.float32, device=a.device)
+    _tapgemm(a=a, a_term_imgs=1, a_imgs=T, a_bcast=0, n_img=1, H=1, W=M, a_H=1, a_W=M, Cc=K,
+             a_sw=a.stride(1), a_sh=a.stride(0), a_sn=a.stride(0),
+             b=w, b_term_g=1, b_groups=w.shape[0], b_batched=0, n_out=Nout, b_sn=w.stride(2), b_sg=w.stride(0),
+             taps=_TAPS_1, d=out, d_mode=OUT_F32, d_strides=(0, 0, Nout, 1), alpha=alpha,
+             k_partials=k_partials, d_slab=M * Nout)
+    return out
+
+
+def splitk_reduce_ln(partials, bias, residual, gamma=None, beta=None, eps=1e-5, *, ln_out=None, row_map=None,
+                     terms=None, want_ln=True):
+    """x = residual + bias + sum_s partials[s] (fixed order) -> (x fp32 [M,C], LayerNorm(x) planes or None).
+    ``ln_out`` / ``row_map``: scatter the normalised rows into an existing planes buffer [T, rows_out, C]."""
+    _need_cuda(partials)
+    S, M, Cc = partials.shape
+    terms = terms or get_terms()
+    x = torch.empty((M, Cc), dtype=torch.float32, device=partials.device)
+    if want_ln and ln_out is None:
+        ln_out = torch.empty((terms, M, Cc), dtype=torch.float16, device=partials.device)
+    ln_rows = ln_out.shape[1] if ln_out is not None else 0
+    _count(1)
+    _lib.check(_lib.load().t2h_splitk_reduce_ln(_ptr(partials), S, M * Cc, _ptr(bias), _ptr(residual), _ptr(x),
+                                                _ptr(gamma), _ptr(beta), eps, _ptr(ln_out) if want_ln else None,
+                                                ln_out.shape[0] if ln_out is not None else terms, _ptr(row_map),
+                                                ln_rows, M, Cc, _stream()))
+    return x, (ln_out if want_ln else None)
 
 
 def wgrad(dy, x, out, k_split=0, alpha=1.0, accumulate=False):

@@ -61,13 +61,52 @@ class VQImageSegmTextureModel(nn.Module):
         return self.decoder.forward_nhwc(conv1x1_nhwc(ops.nchw_to_nhwc(quant), self.post_quant_conv))
 
     @torch.no_grad()
-    def forward_step(self, input, mask, return_info=False):
+    def forward_step(self, input, mask, return_info=False, streams=1):
+        """``streams`` > 1: the batch is cut into that many slices (images are independent on this path) that run
+        concurrently on their own CUDA streams, so one slice's HBM-bound kernels (GroupNorm apply, plane
+        conversions) and small late-level launches overlap the other slice's tensor-bound convolutions."""
+        if streams > 1 and input.shape[0] >= streams and not return_info:
+            return self._forward_step_streams(input, mask, streams)
         r, z = self.encode_nhwc(input, mask)
         dec = self.decoder.forward_nhwc(conv1x1_nhwc(r["zq_nhwc"], self.post_quant_conv))
         if return_info:
             return dec, r["loss"], dict(idx_cont=r["idx_cont"], idx_list=r["idx_list"], z_nhwc=z,
                                         zq_nhwc=r["zq_nhwc"])
         return dec, r["loss"]
+
+    def _forward_step_streams(self, input, mask, streams):
+        B = input.shape[0]
+        main = torch.cuda.current_stream()
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self.__dict__.get("_t2h_streams_sig") != sig:
+            # the packed-weight caches are (re)built on first use: do that once on the current stream, so the
+            # concurrent slices below only read them
+            self.forward_step(input[:1], mask[:1])
+            self.__dict__["_t2h_streams_sig"] = sig
+        pool = self.__dict__.setdefault("_t2h_streams", [])
+        while len(pool) < streams:
+            pool.append(torch.cuda.Stream())
+        cuts = [(B * i) // streams for i in range(streams + 1)]
+        decs, sq = [], []
+        for i in range(streams):
+            st = pool[i]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                xs, ms = input[cuts[i]:cuts[i + 1]], mask[cuts[i]:cuts[i + 1]]
+                r, _ = self.encode_nhwc(xs, ms)
+                d = self.decoder.forward_nhwc(conv1x1_nhwc(r["zq_nhwc"], self.post_quant_conv))
+                decs.append(d)
+                sq.append((r["sqerr"], r["zq_nhwc"].numel()))
+        for i in range(streams):
+            main.wait_stream(pool[i])
+            decs[i].record_stream(main)
+            sq[i][0].record_stream(main)
+        dec = torch.cat(decs, 0)
+        from .vqgan_arch import _loss_from_sqerr
+        tot = sq[0][0].clone()
+        for s_, _ in sq[1:]:
+            tot += s_
+        return dec, _loss_from_sqerr(tot, sum(n for _, n in sq), self.quantize.beta)
 
 
 class HierarchyVQSpatialTextureAwareModel(nn.Module):

@@ -103,6 +103,25 @@ class Block(nn.Module):
             nn.Dropout(resid_pdrop),
         )
 
+    def forward_rows_split(self, x, h, B, T, ks, next_ln, ln_out=None, row_map=None):
+        """Small-batch form of the block (few [128 x 256] output tiles): the two N=C projections (proj, fc2) are
+        split over the contraction so that >= 128 SMs work on them; the k-slices are stored separately and one
+        kernel sums them in a FIXED order (bit-reproducible), adds bias + residual and applies the NEXT LayerNorm.
+        x: fp32 residual stream [M, C]; h: LayerNorm1(x) planes.  -> (x_out fp32, planes of next_ln(x_out))"""
+        a = self.attn
+        Tt, M, Cc = h.shape
+        wqkv, bqkv = a._qkv_packed()
+        qkv = ops.linear(h, wqkv, bqkv, planes_out=True)
+        s = ops.mha_scores(qkv[:, :, :Cc], B, T, a.n_head, k=qkv[:, :, Cc:2 * Cc])
+        p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // a.n_head))
+        y = ops.mha_pv(p, qkv[:, :, 2 * Cc:], B, T, a.n_head, v_tok=True)
+        part = ops.linear_partials(y, _lin_w(a.proj), ks)
+        x, h2 = ops.splitk_reduce_ln(part, _f32(a.proj.bias), x, _f32(self.ln2.weight), _f32(self.ln2.bias), self.ln2.eps)
+        m = ops.linear(h2, _lin_w(self.mlp[0]), _f32(self.mlp[0].bias), planes_out=True, act=ops.ACT_GELU)
+        part = ops.linear_partials(m, _lin_w(self.mlp[2]), ks)
+        return ops.splitk_reduce_ln(part, _f32(self.mlp[2].bias), x, _f32(next_ln.weight), _f32(next_ln.bias),
+                                    next_ln.eps, ln_out=ln_out, row_map=row_map)
+
     def forward_rows(self, x, B, T):
         """x: fp32 [B*T, C] residual stream -> fp32 [B*T, C]"""
         h = ops.layer_norm(x, _f32(self.ln1.weight), _f32(self.ln1.bias), self.ln1.eps)
@@ -184,11 +203,31 @@ class TransformerMultiHead(nn.Module):
         assert T <= self.block_size, "Cannot forward, model block size is exhausted."
         x = ops.embed_sum(idx, segm_tokens, texture_tokens, _f32(self.tok_emb.weight),
                           _f32(self.pos_emb)[0], _f32(self.segm_emb.weight), _f32(self.texture_emb.weight))
-        for block in self.blocks:
-            x = block.forward_rows(x, B, T)
-        h = ops.layer_norm(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), self.ln_f.eps)
+        h = self._trunk(x, B, T)
         logits = ops.linear(h, self._heads_packed())  # [B*T, num_head*head_class_num]
         return logits.view(B, T, self.num_head, self.head_class_num)
+
+    def _trunk(self, x, B, T, ln_out=None, row_map=None):
+        """24 blocks + final LayerNorm of the fp32 stream x [B*T, C] -> planes of ln_f(x) (scattered by ``row_map``
+        into ``ln_out`` for the grouped-head GEMM).  At small batch the deterministic split-K form of the blocks
+        is used (each block's closing kernel already applies the next LayerNorm)."""
+        M, Cc = x.shape
+        ks = ops.wgrad_k_split(M, Cc, Cc) if ops.SPLIT_K["small_batch"] else 0
+        if ks >= 2 and len(self.blocks) > 0:
+            b0 = self.blocks[0]
+            h = ops.layer_norm(x, _f32(b0.ln1.weight), _f32(b0.ln1.bias), b0.ln1.eps)
+            for i, block in enumerate(self.blocks):
+                last = i == len(self.blocks) - 1
+                nxt = self.ln_f if last else self.blocks[i + 1].ln1
+                x, h = block.forward_rows_split(x, h, B, T, ks, nxt, ln_out=ln_out if last else None,
+                                                row_map=row_map if last else None)
+            return h
+        for block in self.blocks:
+            x = block.forward_rows(x, B, T)
+        if ln_out is not None:
+            return ops.layer_norm_scatter(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), ln_out, row_map,
+                                          self.ln_f.eps)
+        return ops.layer_norm(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), self.ln_f.eps)
 
     @staticmethod
     def group_by_texture(texture_tokens, num_head):
@@ -222,9 +261,7 @@ class TransformerMultiHead(nn.Module):
         B, T = idx.shape
         x = ops.embed_sum(idx, segm_tokens, texture_tokens, _f32(self.tok_emb.weight),
                           _f32(self.pos_emb)[0], _f32(self.segm_emb.weight), _f32(self.texture_emb.weight))
-        for block in self.blocks:
-            x = block.forward_rows(x, B, T)
-        ops.layer_norm_scatter(x, _f32(self.ln_f.weight), _f32(self.ln_f.bias), hf_grouped, dest, self.ln_f.eps)
+        self._trunk(x, B, T, ln_out=hf_grouped, row_map=dest)
         Tt, rows_all, Cc = hf_grouped.shape
         rows = rows_all // self.num_head
         w = self._heads_packed().view(Tt, self.num_head, self.head_class_num, Cc)

@@ -708,7 +708,8 @@ class VQGANTrainer:
 
     def _arm(self, sp, on):
         """buckets fire only during the LAST micro-batch's backward of that parameter space"""
-        self._reduce = on and dist.is_initialized() and dist.get_world_size() > 1
+        self._reduce = (on and dist.is_initialized() and dist.get_world_size() > 1 and
+                        not getattr(self, "force_no_reduce", False))
         self._armed = {(id(sp), b): True for b in range(len(sp.buckets))} if self._reduce else {}
 
     def wait_reduced(self):
@@ -783,6 +784,14 @@ class VQGANTrainer:
         self.dec_out.wgrad_only(g_nll, rg)
         self.dec_out.wgrad_only(g_g, gg)
         ops.adaptive_weight(rg, gg, dw, 1.0 / S, self.disc_weight_max, 1.0 if step >= self.disc_start_step else 0.0)
+        import os
+        if os.environ.get("T2H_TRAIN_DEBUG"):
+            print("[train debug] |rg| %.6e |gg| %.6e S %g dw %.6f |g_nll| %.6e |g_g| %.6e" % (
+                float(rg.norm()) / S, float(gg.norm()) / S, S, float(dw[0]), float(g_nll.norm()) / S,
+                float(g_g.norm()) / S))
+            print("[train debug] |xrec| %.8e |xr| %.8e |logits| %.8e |d_lf| %.8e |d_xr| %.8e r %s t %s" % (
+                float(xrec.norm()), float(xr.norm()), float(logits_fake.norm()), float(d_lf.norm()),
+                float(d_xr.norm()) / S, r.tolist(), t.tolist()))
         dxrec = ops.axpy_dev(g_nll, g_g, dw)                 # loss = nll + d_weight * g_loss + codebook_loss
         self._arm(self.gen, last)
         self.gen_backward(dxrec, S)
