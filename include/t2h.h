@@ -254,6 +254,17 @@ int t2h_vq_gather(const float* codebook, const int64_t* idx, const int32_t* book
 int t2h_onehot_to_planes(const float* ids, void* out, int b, int h, int w, int n_classes, int c_pad, int terms,
                          t2h_stream_t stream);
 
+/* Dataset-side preparation (data/segm_attr_dataset.py:120-164) on the device.
+ * texture mask (:138-151): mask = attrs[b][g] + 1 where the parsing class segm value belongs to clothes group
+ * g = cls_group[cls] (0 upper, 1 lower, 2 outer, -1 other) and attrs[b][g] != 17, else 0.  segm/mask float [b][per_img] */
+int t2h_texture_mask(const float* segm, const int32_t* attrs, const int32_t* cls_group, int n_cls, float* mask, int b,
+                     int64_t per_img, t2h_stream_t stream);
+/* uint8 HWC images [b][h][w][c] -> fp16 planes NHWC [terms][b][h][w][c_pad] of x / divisor + shift (image / 127.5 - 1,
+ * :154) -- the operand of Encoder.conv_in -- and optionally (nchw != NULL) the fp32 NCHW tensor the reference's
+ * DataLoader yields */
+int t2h_u8_to_planes(const uint8_t* x, void* out, float* nchw, int b, int h, int w, int c, int c_pad, float divisor,
+                     float shift, int terms, t2h_stream_t stream);
+
 /* nearest-neighbour resize of a float id map [B,1,Hs,Ws] to int32 [B,Ht,Wt]
  * (F.interpolate(mode='nearest'), vqgan_arch.py:222,:385-389) */
 int t2h_mask_to_ids(const float* mask, int32_t* ids, int b, int hs, int ws, int ht,

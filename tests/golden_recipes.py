@@ -144,3 +144,14 @@ def sample_inputs(seed, B):
     g = _gen(seed, "sample_inputs")
     segm_tokens = torch.randint(0, 32, (B, 512), generator=g)
     return segm_tokens, blocky_mask(seed, B, 512, 256, 64)
+
+
+def dataset_items(seed, n, h, w):
+    """synthetic dataset items: uint8 HWC images, parsing maps with class ids 0..23 on 4x4 blocks, fused attributes
+    (upper, lower, outer) in 0..17 (17 = 'NA': that clothes group keeps the common codebook)"""
+    import numpy as np
+    g = _gen(seed, "dataset_items")
+    imgs = torch.randint(0, 256, (n, h, w, 3), generator=g).numpy().astype(np.uint8)
+    seg = torch.randint(0, 24, (n, h // 4, w // 4), generator=g).repeat_interleave(4, 1).repeat_interleave(4, 2)
+    attrs = torch.randint(0, 18, (n, 3), generator=g).numpy().astype(np.int64)
+    return imgs, seg.numpy().astype(np.int64), attrs

@@ -499,6 +499,51 @@ __global__ void onehot_to_planes_kernel(const float* __restrict__ ids, __half* _
   }
 }
 
+// Dataset-side preparation (data/segm_attr_dataset.py:120-164) on the device.
+// texture mask: mask = attr[group(cls)] + 1 where the parsing class belongs to the upper / lower / outer clothes
+// group and that group's fused attribute is not 17 ("NA"), else 0 (:138-151).  cls_group[c] in {-1, 0, 1, 2}.
+__global__ void texture_mask_kernel(const float* __restrict__ segm, const int* __restrict__ attrs,
+                                    const int* __restrict__ cls_group, int n_cls, float* __restrict__ mask,
+                                    long long per_img, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_img);
+    const float v = segm[i];
+    float m = 0.f;
+    if (v == floorf(v) && v >= 0.f && v < (float)n_cls) {
+      const int g = cls_group[(int)v];
+      if (g >= 0) {
+        const int a = attrs[b * 3 + g];
+        if (a != 17) m = (float)(a + 1);
+      }
+    }
+    mask[i] = m;
+  }
+}
+
+// uint8 HWC image batch [B][H][W][C] -> fp16 planes NHWC [terms][B][H][W][c_pad] of x*scale + shift
+// (image / 127.5 - 1, :154, fused with the split the encoder's conv_in needs) and, optionally, the fp32 NCHW
+// tensor the reference's DataLoader would have produced
+__global__ void u8_to_planes_kernel(const unsigned char* __restrict__ x, __half* __restrict__ out,
+                                    float* __restrict__ nchw, int C, int c_pad, long long HW, long long npix,
+                                    float scale, float shift, int terms, long long plane) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    const long long b = p / HW, q = p - b * HW;
+    for (int c = 0; c < c_pad; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        v = __fadd_rn(__fdiv_rn((float)x[p * C + c], scale), shift);   // image / 127.5 - 1: division, then the add
+        if (nchw) nchw[(b * C + c) * HW + q] = v;
+      }
+      __half hi, lo;
+      split_f16(v, hi, lo);
+      out[p * c_pad + c] = hi;
+      if (terms == 2) out[plane + p * c_pad + c] = lo;
+    }
+  }
+}
+
 static inline int grid_for(long long work, int block) {
   long long g = ceil_div64(work, block);
   long long cap = (long long)num_sms() * 16;
@@ -726,6 +771,27 @@ int t2h_onehot_to_planes(const float* ids, void* out, int b, int h, int w, int n
   const long long npix = (long long)b * h * w;
   onehot_to_planes_kernel<<<grid_for(npix * (c_pad / 8), 256), 256, 0, as_stream(stream)>>>(
       ids, reinterpret_cast<__half*>(out), npix, c_pad, n_classes, terms, npix * c_pad);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_texture_mask(const float* segm, const int32_t* attrs, const int32_t* cls_group, int n_cls, float* mask, int b,
+                     int64_t per_img, t2h_stream_t stream) {
+  T2H_CHECK_ARG(segm && attrs && cls_group && mask && b > 0 && per_img > 0 && n_cls > 0, "texture_mask: bad args");
+  const long long total = (long long)b * per_img;
+  texture_mask_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(segm, attrs, cls_group, n_cls, mask,
+                                                                          per_img, total);
+  T2H_LAUNCH_OK();
+  return T2H_OK;
+}
+
+int t2h_u8_to_planes(const uint8_t* x, void* out, float* nchw, int b, int h, int w, int c, int c_pad, float divisor,
+                     float shift, int terms, t2h_stream_t stream) {
+  T2H_CHECK_ARG(x && out && b > 0 && h > 0 && w > 0 && c > 0, "u8_to_planes: bad args");
+  T2H_CHECK_ARG(c_pad >= c && c_pad % 8 == 0 && (terms == 1 || terms == 2) && divisor != 0.f, "u8_to_planes: c_pad/terms");
+  const long long npix = (long long)b * h * w;
+  u8_to_planes_kernel<<<grid_for(npix, 256), 256, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<__half*>(out), nchw, c, c_pad, (long long)h * w, npix, divisor, shift, terms, npix * c_pad);
   T2H_LAUNCH_OK();
   return T2H_OK;
 }

@@ -654,6 +654,45 @@ def onehot_to_planes(segm, n_classes, terms=None):
     return out
 
 
+# clothes groups of the DeepFashion parsing classes (data/segm_attr_dataset.py:63-65): 0 upper, 1 lower, 2 outer
+CLS_GROUP = [-1] * 24
+for _c in (1, 4):
+    CLS_GROUP[_c] = 0
+for _c in (3, 5, 21):
+    CLS_GROUP[_c] = 1
+CLS_GROUP[2] = 2
+
+
+def texture_mask(segm, attrs):
+    """parsing map [B,1,H,W] (float class ids) + fused attributes int [B,3] (upper, lower, outer; 17 = none) ->
+    texture mask [B,1,H,W] float (0 = common codebook, attr+1 = texture codebook), segm_attr_dataset.py:138-151"""
+    _need_cuda(segm, attrs)
+    segm = _f32c(segm)
+    B = segm.shape[0]
+    attrs = attrs.to(torch.int32).contiguous()
+    grp = torch.tensor(CLS_GROUP, dtype=torch.int32, device=segm.device)
+    out = torch.empty_like(segm)
+    _count(1)
+    _lib.check(_lib.load().t2h_texture_mask(_ptr(segm), _ptr(attrs), _ptr(grp), len(CLS_GROUP), _ptr(out), B,
+                                            segm.numel() // B, _stream()))
+    return out
+
+
+def u8_to_planes(img_u8, divisor=127.5, shift=-1.0, want_nchw=False, terms=None):
+    """uint8 [B,H,W,C] -> planes [T,B,H,W,c_pad] of img / divisor + shift (and the fp32 NCHW tensor if asked)"""
+    _need_cuda(img_u8)
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous()
+    B, H, W, Cc = img_u8.shape
+    terms = terms or get_terms()
+    cp = (Cc + 7) // 8 * 8
+    out = torch.empty((terms, B, H, W, cp), dtype=torch.float16, device=img_u8.device)
+    nchw = torch.empty((B, Cc, H, W), dtype=torch.float32, device=img_u8.device) if want_nchw else None
+    _count(1)
+    _lib.check(_lib.load().t2h_u8_to_planes(_ptr(img_u8), _ptr(out), _ptr(nchw), B, H, W, Cc, cp, divisor, shift,
+                                            terms, _stream()))
+    return (out, nchw) if want_nchw else out
+
+
 def mask_to_ids(mask, ht, wt):
     """float id map [B,1,Hs,Ws] -> int32 [B,ht,wt] (nearest)."""
     _need_cuda(mask)

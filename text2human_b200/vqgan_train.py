@@ -620,6 +620,9 @@ class DiscNet(Layer):
             G.wgrad("k4s1", dlp, h, cl.gw, n=N)
             self.tr.done(self.last)
         g = G.dgrad("k4s1", dlp, cl.wt, n=N, in_hw=(hh, ww))
+        dbg = getattr(self, "debug_trace", None)
+        if dbg is not None:
+            dbg.append(("d_h_last", g))
         for conv, bn, kind in reversed(self.mid):
             a, pre, st, hh, ww = rec.pop()
             cp = self.cp(conv)
@@ -631,10 +634,16 @@ class DiscNet(Layer):
                 self.tr.done(bn)
                 G.wgrad(kind, dprep, a, cp.gw, n=N)
                 self.tr.done(conv)
+            if dbg is not None:
+                dbg.append(("dpre", dpre))
             g = G.dgrad(kind, dprep, cp.wt, n=N, in_hw=(hh, ww))
+            if dbg is not None:
+                dbg.append(("d_h", g))
         a0, y0, H, W = rec.pop()
         c0 = self.cp(self.first)
         dpre, dprep = ops.lrelu_bwd(y0, g)
+        if dbg is not None:
+            dbg.append(("dpre0", dpre))
         if want_params:
             self.bias_grad(c0, dpre)
             G.wgrad("k4s2", dprep, a0, c0.gw, n=N)
