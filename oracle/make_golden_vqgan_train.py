@@ -90,7 +90,7 @@ def main():
         m.train()
     B, H, W = cfg["batch"], cfg["enc"]["resolution"], cfg["enc"]["resolution"] // 2
     data = dict(image=R.image(107, B, 3, H, W), texture_mask=R.blocky_mask(108, B, H, W, 8))
-    torch.manual_seed(109)
+    torch.manual_seed(R.VQGAN_TRAIN_AUG_SEED)
     loss, d_loss = fake.training_step(data, cfg["step"])
     gen_params = {}
     for name in ("encoder", "decoder", "quant_conv", "post_quant_conv"):

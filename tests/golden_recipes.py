@@ -130,6 +130,12 @@ TINY_VQGAN_TRAIN = dict(
     dec=dict(in_channels=3, resolution=64, z_channels=32, ch=32, out_ch=3, num_res_blocks=1, attn_resolutions=[8],
              ch_mult=[1, 2, 2, 4], dropout=0.0, resamp_with_conv=True, give_pre_end=False),
     n_embed=64, embed_dim=32, ndf=16, disc_layers=3, disc_start_step=0, step=5, batch=2)
+# Global-RNG seed under which the reference draws DiffAugment's brightness / saturation / contrast / translation for
+# the fixture.  The step's gradient is discontinuous at the LeakyReLU / hinge kinks of the discriminator; the seed was
+# chosen (scan of 109..399 with the restatement) so that no pre-activation of the three discriminator passes is within
+# 7e-5 of a kink -- an fp32-equivalent implementation (activation error ~1e-5) then cannot land on the other side of
+# one, which the first fixture (seed 109: a pre-activation at +1.5e-5) made a coin flip.
+VQGAN_TRAIN_AUG_SEED = 153
 
 
 # reduced index-prediction transformer for the sample_fn fixture: the reference loop hard-codes the 32x16 token grid

@@ -87,12 +87,31 @@ def test_reference_vqgan_wrapper_runs_unmodified_on_the_mirrors(cuda):
     assert torch.equal(cont_m, cont_r)
     assert _rel(dec_m, dec_r) < 1e-3 and abs(float(diff_m) - float(diff_r)) <= 1e-3 * abs(float(diff_r))
 
-    # training: the reference's optimize_parameters, unmodified, with the same RNG stream for DiffAugment
+    # training: the reference's optimize_parameters, unmodified, with the same RNG stream for DiffAugment.
+    # The step's gradient is discontinuous at the discriminator's LeakyReLU / hinge kinks: pick a DiffAugment seed
+    # under which the reference run itself has no pre-activation within 1e-4 of a kink (hooks on the reference disc).
     step = R.TINY_VQGAN_TRAIN["step"]
+    for n in ("encoder", "decoder", "quantize", "quant_conv", "post_quant_conv", "disc"):
+        getattr(wr, n).train()
+    margins = []
+    hooks = [mod.register_forward_pre_hook(lambda m_, inp: margins.append(float(inp[0].detach().abs().min())))
+             for mod in wr.disc.main if isinstance(mod, torch.nn.LeakyReLU)]
+    seed = None
+    for cand in range(31, 80):
+        margins.clear()
+        torch.manual_seed(cand)
+        loss, d_loss = wr.training_step(data, step)
+        if min(margins) > 1e-4:
+            seed = cand
+            break
+    for h_ in hooks:
+        h_.remove()
+    assert seed is not None
+    print(f"[boundary] DiffAugment seed {seed}: min distance of a discriminator pre-activation to its kink {min(margins):.2e}")
     before = {k: v.detach().clone() for k, v in wm.decoder.state_dict().items()}
-    torch.manual_seed(31)
+    torch.manual_seed(seed)
     wm.optimize_parameters(data, step)
-    torch.manual_seed(31)
+    torch.manual_seed(seed)
     wr.optimize_parameters(data, step)
     for k in ("nll_loss", "g_loss", "codebook_loss"):
         assert abs(wm.log_dict[k] - wr.log_dict[k]) <= 2e-4 * max(1.0, abs(wr.log_dict[k])), k

@@ -1036,7 +1036,11 @@ def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=
     nn_, hw = (N, H * W) if n is None else (n, N * H * W // n)
     dx = torch.empty_like(x)
     planes = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device) if want_planes else None
-    ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
+    import os as _os
+    if _os.environ.get("T2H_WS_ZEROS"):
+        ws = torch.zeros((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
+    else:
+        ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
     assert dy.is_contiguous() and x.is_contiguous() and (add is None or add.is_contiguous())
     _count(3)
     _lib.check(_lib.load().t2h_norm_bwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add), _ptr(dx),

@@ -386,18 +386,33 @@ class AttnL(Layer):
         self.b = blk
 
     def _qkv(self):
+        """-> (W [3C, C], dW, b [3C], db): q | k | v as one projection.  In the trainer's flat space the three
+        weights (and biases) are adjacent, so these are views; a space with separate per-conv buffers gets one
+        concatenated copy whose slices REPLACE the per-conv buffers (gradients then land where grad_of looks)."""
         q, k, v = (self.cp(m) for m in (self.b.q, self.b.k, self.b.v))
         Cc = q.co
         sp = self.tr.space_of(self.b.q)
-        off_w = q.w.storage_offset()
-        off_b = q.b.storage_offset()
-        assert k.w.storage_offset() == off_w + Cc * Cc and v.w.storage_offset() == off_w + 2 * Cc * Cc
-        assert k.b.storage_offset() == off_b + Cc and v.b.storage_offset() == off_b + 2 * Cc
+        if hasattr(sp, "flat_p"):
+            off_w = q.w.storage_offset()
+            off_b = q.b.storage_offset()
+            assert k.w.storage_offset() == off_w + Cc * Cc and v.w.storage_offset() == off_w + 2 * Cc * Cc
+            assert k.b.storage_offset() == off_b + Cc and v.b.storage_offset() == off_b + 2 * Cc
 
-        def view(flat, off, r, c):
-            return flat[off:off + r * c].view(r, c)
-        return (view(sp.flat_p, off_w, 3 * Cc, Cc), view(sp.flat_g, off_w, 3 * Cc, Cc),
-                sp.flat_p[off_b:off_b + 3 * Cc], sp.flat_g[off_b:off_b + 3 * Cc])
+            def view(flat, off, r, c):
+                return flat[off:off + r * c].view(r, c)
+            return (view(sp.flat_p, off_w, 3 * Cc, Cc), view(sp.flat_g, off_w, 3 * Cc, Cc),
+                    sp.flat_p[off_b:off_b + 3 * Cc], sp.flat_g[off_b:off_b + 3 * Cc])
+        hit = getattr(self, "_qkv_cat", None)
+        if hit is None:
+            w = torch.cat([c_.w[0] for c_ in (q, k, v)], 0).contiguous()
+            b = torch.cat([c_.b for c_ in (q, k, v)], 0).contiguous()
+            gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+            for i, c_ in enumerate((q, k, v)):
+                c_.w, c_.b = w[i * Cc:(i + 1) * Cc].view(1, Cc, Cc), b[i * Cc:(i + 1) * Cc]
+                if c_.gw is not None:
+                    c_.gw, c_.gb = gw[i * Cc:(i + 1) * Cc].view(1, Cc, Cc), gb[i * Cc:(i + 1) * Cc]
+            hit = self._qkv_cat = (w, gw, b, gb)
+        return hit
 
     def fwd(self, act):
         b = self.b
@@ -575,6 +590,11 @@ class DiscNet(Layer):
             i += 3
         self.last = mods[-1]
 
+    @staticmethod
+    def _dbg(t):
+        # checksum only: holding the tensor itself would change which memory blocks the following ops reuse
+        return torch.stack((t.double().sum(), t.double().abs().sum(), (t.double() ** 2).sum()))
+
     def order(self):
         out = [self.last]
         for conv, bn, _ in reversed(self.mid):
@@ -622,7 +642,7 @@ class DiscNet(Layer):
         g = G.dgrad("k4s1", dlp, cl.wt, n=N, in_hw=(hh, ww))
         dbg = getattr(self, "debug_trace", None)
         if dbg is not None:
-            dbg.append(("d_h_last", g))
+            dbg.append(("d_h_last", self._dbg(g)))
         for conv, bn, kind in reversed(self.mid):
             a, pre, st, hh, ww = rec.pop()
             cp = self.cp(conv)
@@ -635,15 +655,15 @@ class DiscNet(Layer):
                 G.wgrad(kind, dprep, a, cp.gw, n=N)
                 self.tr.done(conv)
             if dbg is not None:
-                dbg.append(("dpre", dpre))
+                dbg.append(("dpre", self._dbg(dpre)))
             g = G.dgrad(kind, dprep, cp.wt, n=N, in_hw=(hh, ww))
             if dbg is not None:
-                dbg.append(("d_h", g))
+                dbg.append(("d_h", self._dbg(g)))
         a0, y0, H, W = rec.pop()
         c0 = self.cp(self.first)
         dpre, dprep = ops.lrelu_bwd(y0, g)
         if dbg is not None:
-            dbg.append(("dpre0", dpre))
+            dbg.append(("dpre0", self._dbg(dpre)))
         if want_params:
             self.bias_grad(c0, dpre)
             G.wgrad("k4s2", dprep, a0, c0.gw, n=N)
