@@ -640,6 +640,28 @@ def run():
                     note="algorithmic FLOPs = 2*MAC of the reference op graph; in fp32 mode each product is "
                          "issued as 3 fp16 tensor-core products (hi*hi+hi*lo+lo*hi), see issued_*")
 
+    # ---------------- the same workload with the per-layer precision map (reported beside the headline) ----------------
+    mixed = None
+    if rank == 0 and world == 1 and not args.no_extra and args.precision == "fp32":
+        ops.set_precision("mixed")
+        try:
+            for i in range(3):
+                model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                model.forward_step(xs_d[i % n_var], ms_d[i % n_var])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_mx = e0.elapsed_time(e1) / args.steps
+            mixed = dict(img_per_s=B / (ms_mx / 1e3), ms_per_step=ms_mx,
+                         pipeline_frac_of_peak=B / (ms_mx / 1e3) * GFLOP_PER_IMG / 1e3 / pk["tf_sustained"],
+                         note="ops.set_precision('mixed'): the six 128-ch 3x3 convs of the decoder's 512x256 level "
+                              "single-product (profiles/r02_precision_map.txt), everything else 3-product; indices "
+                              "bit-identical to the headline mode, pixels within 1e-3 of the reference "
+                              "(tests/test_gpu_baseline_configs.py::test_config2_mixed_precision_map)")
+        finally:
+            ops.set_precision(args.precision)
     # ---------------- side measurements: BASELINE configs 3 and 4 (rank 0, N=1 only) ----------------
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
@@ -696,7 +718,7 @@ def run():
                     e2e=dict(value=e2e_value, unit="img/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, gpu_eager_baseline=eager,
-                    ddp_train=ddp_train, extra=extra,
+                    ddp_train=ddp_train, mixed_precision=mixed, extra=extra,
                     pipeline_tflops=value * GFLOP_PER_IMG / 1e3,
                     pipeline_frac_of_peak=value * GFLOP_PER_IMG / 1e3 / (pk["tf_sustained"] * world))
     if world > 1:

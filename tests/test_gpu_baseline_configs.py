@@ -127,6 +127,32 @@ def test_config2_vqvae_top_full_size(cuda, batch, mask_kind, codebook_kind):
     assert (info["idx_cont"].cpu().numpy() == wq["idx_cont"]).all(), "indices not bit-exact on the kernel's own latent"
 
 
+def test_config2_mixed_precision_map(cuda):
+    """ops.set_precision("mixed") (tools/precision_map.py: the six 128-channel convs of the decoder's full-resolution
+    level single-product, 30 % of the conv FLOPs) at BASELINE config 2's full size: the encoder is untouched, so the
+    indices are those of the parity mode bit for bit; decoded pixels stay within the 1e-3 the north star allows."""
+    from oracle import vqgan_ref
+    from text2human_b200 import ops
+    m, sd, cb = _top_model(cuda, 2021, "trained")
+    batch = 16
+    x = R.image(2021, batch, 3, 512, 256).to(cuda)
+    mask = R.blocky_mask(2021, batch, 512, 256, 32).to(cuda)
+    with torch.no_grad():
+        want = vqgan_ref.vq_forward_step(sd, cb, x, mask)
+    ops.set_precision("fp32")
+    _, _, info32 = m.forward_step(x, mask, return_info=True)
+    ops.set_precision("mixed")
+    try:
+        dec, loss, info = m.forward_step(x, mask, return_info=True)
+    finally:
+        ops.set_precision("fp32")
+    assert torch.equal(info["idx_cont"], info32["idx_cont"]) and torch.equal(info["z_nhwc"], info32["z_nhwc"])
+    assert torch.equal(info["idx_cont"], want["idx_cont"])
+    e2e = _rel(dec, want["dec"])
+    print(f"[config2 mixed] end-to-end pixel rel err {e2e:.2e} (budget 1e-3)")
+    assert e2e < TOL
+
+
 def test_config3_hierarchy_full_size(cuda):
     """BASELINE config 3: vqvae_top + vqvae_bottom nets at 512x256 (B=2 of the benchmarked 8: the path is
     per-image), forward_step = top_encode + bot_encode + decode with the bottom residual."""

@@ -96,18 +96,17 @@ def test_reference_vqgan_wrapper_runs_unmodified_on_the_mirrors(cuda):
     margins = []
     hooks = [mod.register_forward_pre_hook(lambda m_, inp: margins.append(float(inp[0].detach().abs().min())))
              for mod in wr.disc.main if isinstance(mod, torch.nn.LeakyReLU)]
-    seed = None
-    for cand in range(31, 80):
+    best = (0.0, None)
+    for cand in range(31, 71):
         margins.clear()
         torch.manual_seed(cand)
         loss, d_loss = wr.training_step(data, step)
-        if min(margins) > 1e-4:
-            seed = cand
-            break
+        best = max(best, (min(margins), cand))
     for h_ in hooks:
         h_.remove()
-    assert seed is not None
-    print(f"[boundary] DiffAugment seed {seed}: min distance of a discriminator pre-activation to its kink {min(margins):.2e}")
+    margin, seed = best
+    print(f"[boundary] DiffAugment seed {seed}: min distance of a discriminator pre-activation to its kink {margin:.2e}")
+    assert margin > 3e-5
     before = {k: v.detach().clone() for k, v in wm.decoder.state_dict().items()}
     torch.manual_seed(seed)
     wm.optimize_parameters(data, step)
@@ -117,7 +116,8 @@ def test_reference_vqgan_wrapper_runs_unmodified_on_the_mirrors(cuda):
         assert abs(wm.log_dict[k] - wr.log_dict[k]) <= 2e-4 * max(1.0, abs(wr.log_dict[k])), k
     assert abs(float(wm.log_dict["d_weight"]) - float(wr.log_dict["d_weight"])) <= 2e-3 * float(wr.log_dict["d_weight"])
     assert abs(float(wm.log_dict["d_loss"]) - float(wr.log_dict["d_loss"])) <= 2e-4
-    worst = 0.0
+    worst, gmax = 0.0, 0.0
+    pairs = []
     for name in ("encoder", "decoder", "quantize", "quant_conv", "post_quant_conv"):
         pm, pr = dict(getattr(wm, name).named_parameters()), dict(getattr(wr, name).named_parameters())
         assert pm.keys() == pr.keys()
@@ -126,7 +126,17 @@ def test_reference_vqgan_wrapper_runs_unmodified_on_the_mirrors(cuda):
             if gr is None or float(gr.abs().max()) == 0.0:
                 continue
             assert gm is not None, (name, k)
-            worst = max(worst, _rel(gm, gr))
+            pairs.append((f"{name}.{k}", gm, gr))
+            gmax = max(gmax, float(gr.abs().max()))
+    for key, gm, gr in pairs:
+        # gradients that vanish in exact arithmetic (a conv bias in front of a per-channel GroupNorm) are rounding
+        # noise in the reference as well: held to an absolute floor
+        if float(gr.abs().max()) < 1e-6 * gmax:
+            assert float((gm - gr).abs().max()) < 1e-5 * gmax, key
+            continue
+        e = _rel(gm, gr)
+        assert e < 1e-3, (key, e)
+        worst = max(worst, e)
     print(f"[boundary] reference training_step on the mirrors: worst generator gradient rel err {worst:.2e}")
     assert worst < 1e-3
     dworst = 0.0

@@ -19,19 +19,34 @@ from ._lib import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_RELU, CVT_BILINEAR2X, CVT_
 # ----------------------------------------------------------------------------
 # precision policy
 # ----------------------------------------------------------------------------
-_PRECISION = {"terms": 2}
+_PRECISION = {"terms": 2, "mixed": False}
 
 
 def set_precision(mode):
     """"fp32" : hi/lo fp16 planes, 3 tensor-core products per contraction
     (fp32-equivalent; the parity mode).  "fp16": single fp16 plane, one product
-    (10-bit mantissa operands like TF32, fp32 accumulate; the fast mode)."""
+    (10-bit mantissa operands like TF32, fp32 accumulate; the fast mode).
+    "mixed": as "fp32", except that the layers the per-layer precision map clears (tools/precision_map.py,
+    profiles/r02_precision_map.txt: the six 128-channel 3x3 convs of the decoder's full-resolution level, 30 % of
+    all conv FLOPs) run single-product -- decoder pixels stay within 1e-3 of the fp32 reference (measured 6e-4),
+    the encoder and therefore the codebook indices are untouched."""
+    _PRECISION["mixed"] = False
     if mode in ("fp32", "fp16x3", "exact"):
         _PRECISION["terms"] = 2
     elif mode in ("fp16", "fast", "tf32"):
         _PRECISION["terms"] = 1
+    elif mode == "mixed":
+        _PRECISION["terms"] = 2
+        _PRECISION["mixed"] = True
     else:
         raise ValueError(f"unknown precision mode {mode!r}")
+
+
+def layer_terms(mod):
+    """planes per operand for one conv module: 1 where the mixed map marks the layer single-product"""
+    if _PRECISION["mixed"] and getattr(mod, "_t2h_single", False):
+        return 1
+    return _PRECISION["terms"]
 
 
 def get_terms():

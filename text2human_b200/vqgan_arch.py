@@ -43,7 +43,7 @@ def _cached(owner, key, params, build):
 
 
 def _conv_w(conv, c_pad=None):
-    t = ops.get_terms()
+    t = ops.layer_terms(conv)
     return _cached(conv, ("w3", t, c_pad), (conv.weight,),
                    lambda: ops.pack_conv_weight(conv.weight, t, c_pad))
 
@@ -81,10 +81,12 @@ def Normalize(in_channels):
     return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
 
 
-def _gn(act, norm, swish):
+def _gn(act, norm, swish, consumer=None):
+    """``consumer``: the conv that reads the planes (decides how many planes are written)"""
     stats = act.stats if norm.num_groups == ops.GN_GROUPS else None
     return ops.group_norm(act.x, _f32(norm.weight), _f32(norm.bias), swish=swish, groups=norm.num_groups,
-                          eps=norm.eps, stats=stats)
+                          eps=norm.eps, stats=stats,
+                          terms=ops.layer_terms(consumer) if consumer is not None else None)
 
 
 class Upsample(nn.Module):
@@ -164,10 +166,10 @@ class ResnetBlock(nn.Module):
     def _fwd(self, act):
         assert self.dropout.p == 0.0 or not self.training, "dropout>0 in training is not implemented"
         x = act.x
-        a = _gn(act, self.norm1, swish=True)
+        a = _gn(act, self.norm1, swish=True, consumer=self.conv1)
         # conv1's epilogue accumulates the statistics norm2 needs
         h = _Act(*ops.conv3x3(a, _conv_w(self.conv1), _f32(self.conv1.bias), want_stats=True))
-        a = _gn(h, self.norm2, swish=True)
+        a = _gn(h, self.norm2, swish=True, consumer=self.conv2)
         if self.in_channels != self.out_channels:
             xp = ops.f32_to_planes(x, CVT_PLAIN)
             if self.use_conv_shortcut:
@@ -379,6 +381,10 @@ class Decoder(nn.Module):
 
         self.norm_out = Normalize(block_in)
         self.conv_out = torch.nn.Conv2d(block_in, out_ch, kernel_size=3, stride=1, padding=1)
+        # per-layer precision map (ops.set_precision("mixed")): the 3x3 convs of the full-resolution level are the
+        # layers whose single-product error is smallest relative to their FLOPs (nearest the output, least amplified)
+        for blk in self.up[0].block:
+            blk.conv1._t2h_single = blk.conv2._t2h_single = True
 
     def _trunk(self, h, bot_h=None, stop_after_level=None, mid_h=None):
         h = self.mid.block_1._fwd(h)
