@@ -456,6 +456,26 @@ def gpu_eager_baseline(dev, batch=16, steps=3):
                 out[f"config4_{name}"] = dict(ms_per_forward=e0.elapsed_time(e1) / 10, batch=4,
                                               note="model forward only; the reference's sample_fn adds 18 Categorical "
                                                    "draws and ~18 host syncs per step on top")
+            # the reference's own sampling loop (BaseSampleModel.sample_fn, unmodified, stock PyTorch): per-step cost
+            # including its 18 Categorical draws and host synchronisations
+            import types
+            ns2 = RL.install("reference", wrappers=("sample_model",))
+            fake = types.SimpleNamespace(batch_size=4, shape=(32, 16), device=dev, mask_id=18432,
+                                         texture_mask=R.blocky_mask(9, 4, 512, 256, 64).to(dev), segm_tokens=segm,
+                                         sampler_fn=net)
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad():
+                    ns2.sample_model.BaseSampleModel.sample_fn(fake, temp=1.0, sample_steps=2)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    ns2.sample_model.BaseSampleModel.sample_fn(fake, temp=1.0, sample_steps=8)
+                    torch.cuda.synchronize()
+                    ms = (time.perf_counter() - t0) * 1e3 / 8
+                out[f"config4_sample_fn_{name}"] = dict(ms_per_diffusion_step=ms,
+                                                        tokens_per_s_256_steps=2048 / (ms * 256 / 1e3),
+                                                        note="the reference's unmodified sample_fn loop, 8 steps, wall clock")
             del net
             torch.cuda.empty_cache()
     except Exception as exc:

@@ -382,10 +382,11 @@ int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t stream);
 /* Backward of y = act(norm(x)*gamma + beta) for GroupNorm(groups) per image (Normalize(), vqgan_arch.py:510) or,
  * with n = 1 / hw = N*H*W / groups = c, training-mode BatchNorm2d.  stats as t2h_gn_stats / the conv epilogue
  * produced them.  dx = add (optional) + dL/dx; optional fp16 planes of dx; dgamma/dbeta accumulated (may be NULL).
- * ws: 2*n*c doubles of scratch.  act: 0 none, 1 swish, 2 LeakyReLU(0.2). */
+ * ws: 2*n*c doubles of scratch.  act: 0 none, 1 swish, 2 LeakyReLU(0.2).  dx_colsum (optional, [c], accumulated):
+ * column sums of the dx written = the bias gradient of the conv whose output x is. */
 int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
                  const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
-                 int n, int hw, int c, int groups, float eps, int act, t2h_stream_t stream);
+                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, t2h_stream_t stream);
 /* BatchNorm2d running statistics: r = (1-momentum) r + momentum * batch (unbiased variance); stats [c][2] */
 int t2h_bn_update_running(const double* stats, float* running_mean, float* running_var, int64_t count,
                           float momentum, int c, t2h_stream_t stream);

@@ -104,7 +104,7 @@ SIGNATURES = {
     "t2h_embed_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_adam": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
     "t2h_conv_wgrad": (_I, [C.POINTER(ConvWgradParams), _P]),
-    "t2h_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "t2h_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "t2h_bn_update_running": (_I, [_P, _P, _P, _L, _F, _I, _P]),
     "t2h_lrelu_bwd": (_I, [_P, _P, _P, _P, _I, _L, _P]),
     "t2h_sumpool2": (_I, [_P, _P, _I, _I, _I, _I, _P]),

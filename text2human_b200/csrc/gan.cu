@@ -105,9 +105,13 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, const double*
                                       const float* __restrict__ dy, const double* __restrict__ S,
                                       const float* __restrict__ add, float* __restrict__ dx,
                                       __half* __restrict__ planes, int terms, long long plane, int HW, int C,
-                                      int groups, float eps, int act, int pix_per_block) {
-  extern __shared__ float sm[];  // mean, rstd, gamma, beta, m1, m2 [C]
+                                      int groups, float eps, int act, int pix_per_block,
+                                      float* __restrict__ dx_colsum) {
+  extern __shared__ float sm[];  // mean, rstd, gamma, beta, m1, m2, colsum [C]
   float *mean = sm, *rstd = sm + C, *ga = sm + 2 * C, *be = sm + 3 * C, *m1 = sm + 4 * C, *m2 = sm + 5 * C;
+  float* csum = sm + 6 * C;
+  if (dx_colsum)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) csum[c] = 0.f;
   const int n = blockIdx.y;
   norm_consts(stats, gamma, beta, n, C, groups, HW, eps, mean, rstd, ga, be);
   const int cpg = C / groups;
@@ -128,6 +132,10 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, const double*
   const long long p_begin = (long long)blockIdx.x * pix_per_block;
   const long long work = (long long)min((long long)pix_per_block, HW - p_begin) * c4;
   const long long base = ((long long)n * HW + p_begin) * C;
+  // column sums of the dx written (= the bias gradient of the conv that produced x): when blockDim is a multiple of
+  // C/4 a thread always meets the same 4 channels and keeps them in registers
+  const bool fixed_cols = (blockDim.x % c4) == 0;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long i = threadIdx.x; i < work; i += blockDim.x) {
     const int c0 = (int)(i % c4) * 4;
     const long long o = base + i * 4;
@@ -147,6 +155,15 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, const double*
       r[e] = rstd[c] * (du * ga[c] - m1[c] - xh * m2[c]) + as[e];
     }
     *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);
+    if (dx_colsum) {
+      if (fixed_cols) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) cs[e] += r[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(&csum[c0 + e], r[e]);
+      }
+    }
     if (planes) {
       __align__(8) __half hi[4];
       __align__(8) __half lo[4];
@@ -155,6 +172,15 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, const double*
       *reinterpret_cast<uint2*>(planes + o) = *reinterpret_cast<uint2*>(hi);
       if (terms == 2) *reinterpret_cast<uint2*>(planes + plane + o) = *reinterpret_cast<uint2*>(lo);
     }
+  }
+  if (dx_colsum) {
+    if (fixed_cols && threadIdx.x < work) {
+      const int c0 = (int)(threadIdx.x % c4) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(&csum[c0 + e], cs[e]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&dx_colsum[c], csum[c]);
   }
 }
 
@@ -490,7 +516,7 @@ extern "C" {
 
 int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
                  const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
-                 int n, int hw, int c, int groups, float eps, int act, t2h_stream_t stream) {
+                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, t2h_stream_t stream) {
   T2H_CHECK_ARG(x && stats && gamma && beta && dy && dx && ws && n > 0 && hw > 0, "norm_bwd: bad args");
   T2H_CHECK_ARG(c % groups == 0 && c % 4 == 0 && c <= 2048, "norm_bwd: C=%d groups=%d unsupported", c, groups);
   T2H_CHECK_ARG(act >= 0 && act <= 2 && (terms == 1 || terms == 2 || !dx_planes), "norm_bwd: act=%d terms=%d", act,
@@ -514,9 +540,9 @@ int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const 
   int ppb2 = ceil_div(hw, bx2);
   if (ppb2 < 16) ppb2 = 16;
   bx2 = ceil_div(hw, ppb2);
-  norm_bwd_apply_kernel<<<dim3(bx2, n), 256, 6 * c * sizeof(float), st>>>(
+  norm_bwd_apply_kernel<<<dim3(bx2, n), 256, 7 * c * sizeof(float), st>>>(
       x, stats, gamma, beta, dy, ws, add, dx, reinterpret_cast<__half*>(dx_planes), terms, (long long)n * hw * c, hw,
-      c, groups, eps, act, ppb2);
+      c, groups, eps, act, ppb2, dx_colsum);
   T2H_LAUNCH_OK();
   if (dgamma && dbeta) {
     norm_bwd_params_kernel<<<ceil_div(c, 128), 128, 0, st>>>(ws, dgamma, dbeta, n, c);

@@ -60,6 +60,8 @@ struct TapGemmDev {
   // images, both operands are NHWC planes read MN-major, the output "image" index is the tap whose (dy, dx,
   // img_off) shifts the X patch; accum: the epilogue reduce-adds into D even without split-K
   int wg, accum;
+  int wg_pair, wg_ntaps;  // wg_pair: one 128 x 256 tile holds TWO taps side by side (Cin <= 128: N = 256 MMAs run at
+                          // the full tensor rate, N = 128 at half of it); image index = tap pair
   int partials;  // split-K without reduction: k-slice s of a tile is stored to image slot t.img + s of D
   int wg_PW, wg_PH, wg_pw, wg_ppi;
   int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
@@ -318,6 +320,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   } else if (P.b_mn) {
                     // [k][column] storage: one box of 64 columns x 64 k per 64 output columns
                     int c1 = ch * kBK, c2 = b_g + P.g_btap[g][tp] + pl * P.b_term_g, c3 = b_g2;
+                    if (P.wg && P.wg_pair) {
+                      // two taps per tile: 64-column boxes 0,1 hold tap 2*img, boxes 2,3 tap 2*img + 1 (the last
+                      // pair of an odd tap count re-reads the last tap; its columns are never stored)
+                      const int n = ch / P.wg_ppi, r = ch - n * P.wg_ppi, py = r / P.wg_pw, px = r - py * P.wg_pw;
+                      for (int q = 0; q < BN / 64; ++q) {
+                        int tap = 2 * t.img + (q >> 1);
+                        if (tap >= P.wg_ntaps) tap = P.wg_ntaps - 1;
+                        tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, 64 * (q & 1),
+                                    px * P.wg_PW + P.wg_dx[tap], py * P.wg_PH + P.wg_dy[tap],
+                                    n + P.wg_ioff[tap] + pl * P.b_term_g);
+                      }
+                    } else {
                     if (P.wg) {  // the same patch of X, shifted by this output tile's tap
                       const int n = ch / P.wg_ppi, r = ch - n * P.wg_ppi, py = r / P.wg_pw, px = r - py * P.wg_pw;
                       c1 = px * P.wg_PW + P.wg_dx[t.img]; c2 = py * P.wg_PH + P.wg_dy[t.img];
@@ -325,6 +339,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     for (int q = 0; q < BN / 64; ++q)
                       tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot + q * 8192, t.n0 + 64 * q, c1, c2, c3);
+                    }
                   } else {
                     tma_load_4d(&tmB, &b_full[sb], b_ring + sb * C::kBSlot, ch * kBK, t.n0,
                                 b_g + P.g_btap[g][tp] + pl * P.b_term_g, b_g2);
@@ -447,7 +462,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (P.epi_mode == EPI_TMA_F32) {
         // ---- fp32 NHWC output: 32-column units through swizzled smem + TMA store
         const int cols_left = P.n_out - t.n0;
-        const int nuc = (cols_left >= BN) ? BN / 32 : (cols_left + 31) / 32;
+        int nuc = (cols_left >= BN) ? BN / 32 : (cols_left + 31) / 32;
+        if (P.wg_pair && 2 * t.img + 1 >= P.wg_ntaps) nuc = BN / 64;  // odd tap count: the last tile's upper half is unused
         const int nunits = MBLK * nuc;
         const bool has_res = P.residual != nullptr;
         auto issue_res = [&](int u, int b) {
@@ -541,7 +557,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           named_bar_sync(2, 128);  // staging tile complete; residual tile fully consumed
           if (elected) {
-            if (P.partials)  // deterministic split-K: every k-slice owns a slab; a fixed-order pass sums them
+            if (P.wg_pair)   // unit cc of a two-tap tile: columns (cc & 3) * 32 of tap 2*img + (cc >> 2)
+              tma_reduce_add_4d(&tmD, ob, (cc & (BN / 64 - 1)) * 32, t.w0, t.h0 + mb * P.TH, 2 * t.img + cc / (BN / 64));
+            else if (P.partials)  // deterministic split-K: every k-slice owns a slab; a fixed-order pass sums them
               tma_store_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img + work / P.total_tiles);
             else if (P.ksplit > 1 || P.accum)
               tma_reduce_add_4d(&tmD, ob, col0, t.w0, t.h0 + mb * P.TH, t.img);  // partial sum of a k-slice
@@ -1171,7 +1189,23 @@ extern "C" int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t strea
   int BN = p->cin <= 64 ? 64 : (p->cin <= 128 ? 128 : 256);
   P.tiles_w = ceil_div(p->cout, 128); P.tiles_h = 1;
   P.n_tiles_n = ceil_div(p->cin, BN);
-  P.total_tiles = p->ntaps * P.tiles_w * P.n_tiles_n;
+  P.wg_ntaps = p->ntaps;
+  {
+    static int no_pair = -1;
+    if (no_pair < 0) {
+      const char* e = getenv("T2H_WGRAD_NO_PAIR");
+      no_pair = e ? atoi(e) : 0;
+    }
+    // 65..128 input channels: two taps share one 128 x 256 tile, so the MMAs issue with N = 256 (full rate)
+    if (!no_pair && p->cin > 64 && p->cin <= 128 && p->ntaps >= 2) {
+      P.wg_pair = 1;
+      BN = 256;
+      P.n_tiles_n = 1;
+      P.n_img = ceil_div(p->ntaps, 2);
+      P.n_out = 256;
+    }
+  }
+  P.total_tiles = P.n_img * P.tiles_w * P.n_tiles_n;
   P.epi_mode = EPI_TMA_F32;
   int ks = p->k_split > 0 ? p->k_split : num_sms() / P.total_tiles;
   if (ks < 1) ks = 1;

@@ -1043,8 +1043,9 @@ def norm_stats(x, groups, n=None):
 
 
 def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=None, add=None, want_planes=False,
-             n=None, terms=None):
-    """backward of act(norm(x)*gamma+beta): -> dx fp32 (+ add) [, planes of dx]; dgamma/dbeta accumulated"""
+             n=None, terms=None, colsum_out=None):
+    """backward of act(norm(x)*gamma+beta): -> dx fp32 (+ add) [, planes of dx]; dgamma/dbeta accumulated;
+    ``colsum_out`` [C] += column sums of dx (the bias gradient of the conv that produced x)"""
     _need_cuda(x, dy)
     N, H, W, Cc = x.shape
     terms = terms or get_terms()
@@ -1060,7 +1061,7 @@ def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=
     _count(3)
     _lib.check(_lib.load().t2h_norm_bwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add), _ptr(dx),
                                         _ptr(planes), terms, _ptr(dgamma), _ptr(dbeta), _ptr(ws), nn_, hw, Cc, groups,
-                                        eps, ACT_CODE[act], _stream()))
+                                        eps, ACT_CODE[act], _ptr(colsum_out), _stream()))
     return (dx, planes) if want_planes else dx
 
 

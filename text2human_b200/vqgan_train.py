@@ -176,11 +176,12 @@ class Act:
 
 
 class Grad:
-    """gradient wrt an activation: fp32 NHWC + (optionally) its fp16 planes"""
-    __slots__ = ("g", "p")
+    """gradient wrt an activation: fp32 NHWC + (optionally) its fp16 planes and its column sums (what the producing
+    norm-backward kernel accumulated on the side: the bias gradient of the conv this activation came out of)"""
+    __slots__ = ("g", "p", "colsum")
 
-    def __init__(self, g, p=None):
-        self.g, self.p = g, p
+    def __init__(self, g, p=None, colsum=None):
+        self.g, self.p, self.colsum = g, p, colsum
 
     def planes(self):
         if self.p is None:
@@ -203,9 +204,16 @@ class Layer:
     def gof(self, p):
         return self.tr.space_of_param(p).g(p)
 
-    def bias_grad(self, cp, g_nhwc):
-        if cp.gb is not None:
-            ops.colsum_(cp.gb[:g_nhwc.shape[-1]], g_nhwc.reshape(-1, g_nhwc.shape[-1]))
+    def bias_grad(self, cp, g):
+        """cp.gb += column sums of the output gradient ``g`` (a Grad, or a bare fp32 NHWC tensor)"""
+        if cp.gb is None:
+            return
+        t = g.g if isinstance(g, Grad) else g
+        Cc = t.shape[-1]
+        if isinstance(g, Grad) and g.colsum is not None:
+            ops.add_inplace(cp.gb[:Cc], g.colsum)
+        else:
+            ops.colsum_(cp.gb[:Cc], t.reshape(-1, Cc))
 
 
 class ConvL(Layer):
@@ -234,7 +242,7 @@ class ConvL(Layer):
         a, N, H, W = self.saved.pop()
         cp = self.cp(self.conv)
         dyp = grad.planes()
-        self.bias_grad(cp, grad.g)
+        self.bias_grad(cp, grad)
         G.wgrad(self.kind, dyp, a, cp.gw, n=N)
         self.tr.done(self.conv)
         if not self.need_dx:
@@ -263,7 +271,7 @@ class ConvInImageL(Layer):
     def bwd(self, grad):
         a, N = self.saved.pop()
         cp = self.cp(self.conv)
-        self.bias_grad(cp, grad.g)
+        self.bias_grad(cp, grad)
         G.wgrad("k3", grad.planes(), a, cp.gw, n=N)
         self.tr.done(self.conv)
         return None
@@ -308,11 +316,12 @@ class NormConvOutL(Layer):
         G.wgrad("k3", dyp, a, cp.gw, n=N)
         self.tr.done(self.conv)
         da = G.dgrad("k3", dyp, cp.wt, n=N, in_hw=(H, W))
+        cs = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
         dx, dxp = ops.norm_bwd(x, st, self.norm.weight.detach(), self.norm.bias.detach(), da, act="swish", groups=32,
                                eps=self.norm.eps, dgamma=self.gof(self.norm.weight), dbeta=self.gof(self.norm.bias),
-                               want_planes=True)
+                               want_planes=True, colsum_out=cs)
         self.tr.done(self.norm)
-        return Grad(dx, dxp)
+        return Grad(dx, dxp, cs)
 
 
 class ResL(Layer):
@@ -349,16 +358,16 @@ class ResL(Layer):
         x, st1, a1, h1, st2, a2, xp, N, H, W = self.saved.pop()
         c1, c2 = self.cp(b.conv1), self.cp(b.conv2)
         dop = grad.planes()
-        self.bias_grad(c2, grad.g)
+        self.bias_grad(c2, grad)
         G.wgrad("k3", dop, a2, c2.gw, n=N)
         self.tr.done(b.conv2)
         d_a2 = G.dgrad("k3", dop, c2.wt, n=N, in_hw=(H, W))
         d_h1, d_h1p = ops.norm_bwd(h1, st2, b.norm2.weight.detach(), b.norm2.bias.detach(), d_a2, act="swish",
                                    groups=32, eps=b.norm2.eps, dgamma=self.gof(b.norm2.weight),
-                                   dbeta=self.gof(b.norm2.bias), want_planes=True)
+                                   dbeta=self.gof(b.norm2.bias), want_planes=True,
+                                   colsum_out=c1.gb[:h1.shape[-1]] if c1.gb is not None else None)   # conv1's bias gradient
         self.tr.done(b.norm2)
         del d_a2, a2, h1
-        self.bias_grad(c1, d_h1)
         G.wgrad("k3", d_h1p, a1, c1.gw, n=N)
         self.tr.done(b.conv1)
         d_a1 = G.dgrad("k3", d_h1p, c1.wt, n=N, in_hw=(H, W))
@@ -366,15 +375,16 @@ class ResL(Layer):
         d_sc = grad.g
         if xp is not None:
             cs = self.cp(b.nin_shortcut)
-            self.bias_grad(cs, grad.g)
+            self.bias_grad(cs, grad)
             G.wgrad("k1", dop, xp, cs.gw, n=N)
             self.tr.done(b.nin_shortcut)
             d_sc = G.dgrad("k1", dop, cs.wt, n=N, in_hw=(H, W))
+        csum = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
         dx, dxp = ops.norm_bwd(x, st1, b.norm1.weight.detach(), b.norm1.bias.detach(), d_a1, act="swish", groups=32,
                                eps=b.norm1.eps, dgamma=self.gof(b.norm1.weight), dbeta=self.gof(b.norm1.bias),
-                               add=d_sc, want_planes=True)
+                               add=d_sc, want_planes=True, colsum_out=csum)
         self.tr.done(b.norm1)
-        return Grad(dx, dxp)
+        return Grad(dx, dxp, csum)
 
 
 class AttnL(Layer):
@@ -442,7 +452,7 @@ class AttnL(Layer):
         scale = float(int(Cc) ** (-0.5))
         cpo = self.cp(b.proj_out)
         dop = grad.planes().view(T, M, Cc)
-        self.bias_grad(cpo, grad.g)
+        self.bias_grad(cpo, grad)
         ops.wgrad(dop, o, cpo.gw[0], k_split=ops.wgrad_k_split(Cc, Cc, M), accumulate=True)
         self.tr.done(b.proj_out)
         d_o = ops.linear(dop, cpo.wn, w_kn=True, planes_out=True)                       # planes [T,M,C] = dY Wp
@@ -461,11 +471,12 @@ class AttnL(Layer):
         for m_ in (b.q, b.k, b.v):
             self.tr.done(m_)
         d_hn = ops.linear(dqkvp, wp, w_kn=True)                                         # [M, C]
+        csum = torch.zeros(Cc, dtype=torch.float32, device=x.device)
         dx, dxp = ops.norm_bwd(x, st, b.norm.weight.detach(), b.norm.bias.detach(), d_hn.view(N, H, W, Cc), act=None,
                                groups=32, eps=b.norm.eps, dgamma=self.gof(b.norm.weight),
-                               dbeta=self.gof(b.norm.bias), add=grad.g, want_planes=True)
+                               dbeta=self.gof(b.norm.bias), add=grad.g, want_planes=True, colsum_out=csum)
         self.tr.done(b.norm)
-        return Grad(dx, dxp)
+        return Grad(dx, dxp, csum)
 
 
 class Lin1x1L(Layer):
@@ -487,7 +498,7 @@ class Lin1x1L(Layer):
         a, N, H, W = self.saved.pop()
         cp = self.cp(self.conv)
         dyp = grad.planes()
-        self.bias_grad(cp, grad.g)
+        self.bias_grad(cp, grad)
         G.wgrad("k1", dyp, a, cp.gw, n=N)
         self.tr.done(self.conv)
         return Grad(G.dgrad("k1", dyp, cp.wt, n=N, in_hw=(H, W)))

@@ -43,9 +43,13 @@ def bench(kind, N, H, W, Ci, Co, terms):
     return out
 
 
-for (kind, N, H, W, Ci, Co) in [("k3", 8, 512, 256, 128, 128), ("k3", 8, 256, 128, 128, 128), ("k3", 8, 128, 64, 256, 256),
-                                ("k3", 8, 32, 16, 512, 512), ("down", 8, 512, 256, 128, 128), ("k4s2", 8, 256, 128, 64, 128)]:
-    for terms in (1, 2):
+CASES = os.environ.get("CASES")          # e.g. CASES=0 -> only the first shape (ncu capture target)
+TERMS = [int(t) for t in os.environ.get("TERMS", "1,2").split(",")]
+for ci_, (kind, N, H, W, Ci, Co) in enumerate([("k3", 8, 512, 256, 128, 128), ("k3", 8, 256, 128, 128, 128), ("k3", 8, 128, 64, 256, 256),
+                                ("k3", 8, 32, 16, 512, 512), ("down", 8, 512, 256, 128, 128), ("k4s2", 8, 256, 128, 64, 128)]):
+    if CASES is not None and str(ci_) not in CASES.split(","):
+        continue
+    for terms in TERMS:
         r = bench(kind, N, H, W, Ci, Co, terms)
         print(f"{kind} {N}x{H}x{W} {Ci}->{Co} terms={terms}: " +
               "  ".join(f"{k} {v[0] * 1e3:8.1f} us {v[1]:7.1f} TF/s" for k, v in r.items()), flush=True)
