@@ -73,25 +73,36 @@ def _worker(rank, world, port, q):
         t1.gen.adam(t1.lr, t1.betas, t1.eps, 1.0 / (2 * t1.loss_scale))
         big = t1.gen.flat_g.abs() > 1e-3 * t1.gen.flat_g.abs().max()     # Adam amplifies rounding noise of ~zero grads
         out["p_dev"] = float((tr.gen.flat_p - t1.gen.flat_p)[big].abs().max())
-    q.put(out)
+    import json
+    with open(os.path.join(q, f"rank{rank}.json"), "w") as f:     # q: a directory; plain files instead of an mp.Queue
+        json.dump(out, f)
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
+    os._exit(0)        # skip interpreter teardown (CUDA / NCCL atexit handlers of a spawned worker can stall it)
 
 
-def test_two_rank_gradients_equal_single_process_micro_batches(cuda):
+def test_two_rank_gradients_equal_single_process_micro_batches(cuda, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    import json
+    import time
     port = _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda r: r["rank"])
+    files = [os.path.join(str(tmp_path), f"rank{r}.json") for r in range(2)]
+    t0 = time.time()
+    while not all(os.path.exists(f) for f in files) and time.time() - t0 < 600 and all(p.is_alive() or p.exitcode == 0 for p in procs):
+        time.sleep(0.5)
+    time.sleep(1.0)
+    assert all(os.path.exists(f) for f in files), [p.exitcode for p in procs]
+    r0, r1 = (json.load(open(f)) for f in files)
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
-    r0, r1 = res
+        p.join(timeout=60)
+        if p.is_alive():
+            p.kill()
     print(f"[ddp] buckets {r0['n_buckets']} all-reduces launched during backward {r0['n_reduces']}; gradient rel diff "
           f"generator {r0['gen_rel']:.2e} discriminator {r0['dsc_rel']:.2e}; parameter deviation after Adam {r0['p_dev']:.2e}")
     assert r0["n_reduces"] == r0["n_buckets"] >= 4

@@ -391,6 +391,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
+    // a gradient that overflowed the fp16 operand planes of the backward GEMMs (static loss scale) arrives as inf / NaN:
+    // leave that element's parameter and moments untouched instead of poisoning them for good
+    if (!isfinite(gi)) continue;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -561,8 +564,9 @@ int t2h_embed_bwd(const float* dx, const int64_t* idx, float* de, int64_t rows, 
 int t2h_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
              float eps, int step, float grad_scale, t2h_stream_t stream) {
   T2H_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adam: bad args");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  // bias corrections in double (as torch does): 1 - beta^step loses ~1e-5 relative in fp32 at small step counts
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<grid1d(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s,
                                                             grad_scale);
   T2H_LAUNCH_OK();

@@ -295,6 +295,9 @@ class SamplerTrainer:
     # ------------------------------------------------------------------ optimiser
     def adam_step(self):
         """torch.optim.Adam(lr, weight_decay=0) on the flat buffers; gradients averaged over ranks"""
+        p0 = self.m.tok_emb.weight
+        assert p0.data_ptr() == self.flat_p.data_ptr() + 4 * self.gview[id(p0)].storage_offset(), \
+            "the model's parameters no longer alias the trainer's flat buffer (model.to() / .half() after construction?)"
         self.step_count += 1
         world = dist.get_world_size() if dist.is_initialized() else 1
         ops.adam_(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1],
