@@ -324,6 +324,34 @@ def vqgan_train_workload(dev, precision, rank, world, global_batch=64, micro=8, 
         ms_nr = timed(steps, False)[0] if world > 1 else ms
         tr.force_no_reduce = False
         loss = tr.losses()
+        # roofline of the step's tensor-core launches (instrumented pass, rank 0): forward / data-gradient tap-GEMMs and
+        # the weight-gradient launches, algorithmic FLOPs over their summed CUDA-event time
+        kern = None
+        if rank == 0:
+            ops.profile_tapgemm(True)
+            tr.force_no_reduce = True
+            tr.training_step(data, 99, gen)
+            tr.wait_reduced()
+            torch.cuda.synchronize()
+            tr.force_no_reduce = False
+            agg = {}
+            for algo, issued, a, b, shape in ops.profile_records():
+                k = "wgrad" if shape[0] == "wgrad" else "fwd_dgrad"
+                t = a.elapsed_time(b)
+                e = agg.setdefault(k, [0, 0.0, 0.0])
+                e[0] += 1; e[1] += t; e[2] += algo
+            ops.profile_tapgemm(False)
+            pk_ = peaks()
+            kern = {k: dict(launches=v[0], ms=v[1], algorithmic_tflops=v[2] / v[1] / 1e9,
+                            frac=v[2] / v[1] / 1e9 / pk_["tf_sustained"]) for k, v in agg.items()}
+            tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                kern["wgrad_traffic"] = dict(dram_bytes_per_launch=tj["dram_bytes_per_launch"],
+                                             algorithmic_bytes_per_launch=tj["algorithmic_bytes_per_launch"],
+                                             kernel=tj["kernel"], source=tj["source"])
+        if world > 1:
+            dist.barrier()
         gflop_img = 3 * GFLOP_PER_IMG                    # generator forward + data + weight gradients (2*MAC)
         return dict(global_batch=global_batch, per_gpu_batch=per_gpu, micro_batch=mb, n_gpus=world, scaling="strong",
                     ms_per_step=ms, img_per_s=global_batch / (ms / 1e3), launches_per_step=launches,
@@ -335,7 +363,7 @@ def vqgan_train_workload(dev, precision, rank, world, global_batch=64, micro=8, 
                                           "backward kernel, so its reduction cannot overlap anything"),
                     algorithmic_tflops=global_batch * gflop_img / ms, precision=precision,
                     frac_of_peak=global_batch * gflop_img / ms / (peaks()["tf_sustained"] * world),
-                    losses={k: float(v) for k, v in loss.items()},
+                    losses={k: float(v) for k, v in loss.items()}, tensor_kernels=kern,
                     note="LPIPS stubbed (config 5); BatchNorm / adaptive weight per micro-batch = per DDP rank")
     finally:
         ops._PRECISION["terms"] = old_terms
@@ -657,8 +685,11 @@ def run():
                     algorithmic_tflop_per_step=algo / 1e12,
                     issued_tensor_tflops=issued / (t_ms * 1e-3) / 1e12,
                     issued_frac=issued / (t_ms * 1e-3) / 1e12 / pk["tf_sustained"],
-                    note="algorithmic FLOPs = 2*MAC of the reference op graph; in fp32 mode each product is "
-                         "issued as 3 fp16 tensor-core products (hi*hi+hi*lo+lo*hi), see issued_*")
+                    note="achieved = algorithmic FLOPs of the tap-GEMM launches AS EXECUTED (2*MAC; the reference's "
+                         "nearest-x2 + 3x3 Upsample convs run folded into four 2x2 convs, so 11.71 TFLOP per batch "
+                         "instead of the reference op graph's 12.55 that pipeline_tflops uses) / their summed CUDA-event "
+                         "time; in fp32 mode each product is issued as 3 fp16 tensor-core products "
+                         "(hi*hi+hi*lo+lo*hi), see issued_*")
 
     # ---------------- the same workload with the per-layer precision map (reported beside the headline) ----------------
     mixed = None

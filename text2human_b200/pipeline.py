@@ -67,8 +67,9 @@ class VQImageSegmTextureModel(nn.Module):
         conversions) and small late-level launches overlap the other slice's tensor-bound convolutions."""
         if streams > 1 and input.shape[0] >= streams and not return_info:
             return self._forward_step_streams(input, mask, streams)
-        r, z = self.encode_nhwc(input, mask)
-        dec = self.decoder.forward_nhwc(conv1x1_nhwc(r["zq_nhwc"], self.post_quant_conv))
+        with ops.stats_arena(input.shape[0], input.device):   # one fill for all fused GroupNorm statistics of the step
+            r, z = self.encode_nhwc(input, mask)
+            dec = self.decoder.forward_nhwc(conv1x1_nhwc(r["zq_nhwc"], self.post_quant_conv))
         if return_info:
             return dec, r["loss"], dict(idx_cont=r["idx_cont"], idx_list=r["idx_list"], z_nhwc=z,
                                         zq_nhwc=r["zq_nhwc"])
