@@ -30,8 +30,8 @@ def _worker(rank, world, port, q):
     D.barrier()
     t = D.max_over_ranks(1.0 + rank)
     n = D.sum_over_ranks(xs.shape[0])
-    if rank == 0:
-        q.put((full, t, n, xs.shape[0]))
+    if rank == 0:   # plain python values: a tensor in the queue is a shared-memory handle that dies with this process
+        q.put((full.numpy().tolist(), t, n, xs.shape[0]))
     torch.distributed.destroy_process_group()
 
 
@@ -49,7 +49,7 @@ def test_replica_sharding_two_ranks_gloo():
     g = torch.Generator().manual_seed(0)
     x = torch.randn(7, 3, 4, 4, generator=g)
     want = x * 2 + torch.arange(7).float().view(7, 1, 1, 1)
-    assert torch.equal(full, want)
+    assert torch.equal(torch.tensor(full), want)
     assert t == 2.0 and n == 7 and n0 == 4
 
 
@@ -87,7 +87,7 @@ def _train_worker(rank, world, port, q):
     n_handles = len(tr._handles)
     tr.wait_reduced()
     if rank == 0:
-        q.put((tr.flat_g.clone(), n_handles))
+        q.put((tr.flat_g.numpy().tolist(), n_handles))
     torch.distributed.destroy_process_group()
 
 
@@ -99,6 +99,7 @@ def test_trainer_gradient_buckets_cover_flat_buffer_gloo():
     for p in procs:
         p.start()
     g, n_handles = q.get(timeout=120)
+    g = torch.tensor(g, dtype=torch.float32)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

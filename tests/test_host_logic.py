@@ -108,11 +108,15 @@ def test_group_by_texture_places_every_position_once_inside_its_head_group():
 
 def test_split_k_switches_and_choice():
     from text2human_b200 import ops
-    assert ops.SPLIT_K == {"wgrad": True, "inference": False}
+    assert ops.SPLIT_K == {"wgrad": True, "inference": False, "small_batch": True}
     old = ops.set_split_k(inference=True, wgrad=False)
-    assert ops.SPLIT_K == {"wgrad": False, "inference": True} and old == {"wgrad": True, "inference": False}
+    assert ops.SPLIT_K == {"wgrad": False, "inference": True, "small_batch": True}
+    assert old == {"wgrad": True, "inference": False, "small_batch": True}
     ops.set_split_k(**old)
     assert ops.SPLIT_K == old
+    # the deterministic (stored-partials) form: slices the kernel produces for a k_partials request
+    assert ops.split_slices(512, 4) == 4 and ops.split_slices(2048, 4) == 4 and ops.split_slices(64, 4) == 1
+    assert ops.split_slices(8 * 64, 3) == 3 and ops.split_slices(7 * 64, 4) == 4 and ops.split_slices(5 * 64, 4) == 3
     assert ops.wgrad_k_split(512, 512, 8192) == 18        # 8 output tiles: up to 148 // 8 slices (the kernel
                                                           # rounds to 16 slices of 8 chunks)
     assert ops.wgrad_k_split(18432, 512, 8192) == 0       # 288 tiles already fill the GPU
