@@ -1,0 +1,96 @@
+"""GPU: GroupNorm + swish folded into the consuming conv's activation producer (tapgemm_swap_kernel<MBLK, true>;
+Normalize() + nonlinearity() + Conv2d of ResnetBlock / conv_out, vqgan_arch.py:599-609, :916-918, :1030-1032) against
+the two-launch form (gn_apply pass + conv): the slabs are built with the same arithmetic, so results are identical bit
+for bit; and against torch fp64 for absolute accuracy."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import golden_recipes as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, ref):
+    got, ref = got.double(), ref.double()
+    return ((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+CASES = [  # N, H, W, Cin, Cout, terms, residual, nchw
+    (2, 32, 16, 128, 128, 2, True, False), (1, 64, 32, 128, 256, 2, False, False), (2, 16, 8, 256, 256, 2, True, False),
+    (2, 8, 4, 256, 128, 2, False, False), (2, 32, 16, 128, 3, 2, False, True), (2, 32, 16, 128, 128, 1, True, False),
+    (3, 40, 24, 64, 128, 2, False, False), (1, 256, 128, 128, 128, 2, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(str(int(v)) for v in c))
+def test_fused_gn_conv_equals_two_launch_form(cuda, case):
+    from text2human_b200 import ops
+    N, H, W, Ci, Co, terms, residual, nchw = case
+    g = torch.Generator().manual_seed(sum(int(v) for v in case))
+    x = (torch.randn(N, H, W, Ci, generator=g) * 1.5 + 0.3).to(cuda)
+    gamma = (1 + 0.1 * torch.randn(Ci, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(Ci, generator=g)).to(cuda)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5
+    b = (0.1 * torch.randn(Co, generator=g)).to(cuda)
+    res = torch.randn(N, H, W, Co, generator=g).to(cuda) if residual else None
+    wp = ops.pack_conv_weight(w.to(cuda), terms)
+    stats = ops.norm_stats(x, 32)
+    old = ops.set_fuse_gn(True)
+    try:
+        assert ops.can_fuse_gn(Ci, Co, W, 32, nchw_out=nchw)
+    finally:
+        ops.set_fuse_gn(old)
+    fused = ops.conv3x3_gn(x, stats, gamma, beta, wp, b, eps=1e-6, swish=True, residual=res, nchw_out=nchw,
+                           want_stats=not nchw)
+    a = ops.group_norm(x, gamma, beta, swish=True, eps=1e-6, terms=terms, stats=stats)
+    plain = ops.conv3x3(a, wp, b, residual=res, nchw_out=nchw, want_stats=not nchw)
+    if not nchw:
+        (fused, fstats), (plain, pstats) = fused, plain
+        if pstats is not None:
+            assert _rel(fstats, pstats) < 1e-5      # float shared-memory atomics: summation order varies
+    assert torch.equal(fused, plain), f"max diff {float((fused - plain).abs().max()):.3e}"
+    # absolute accuracy vs fp64 torch
+    xr = x.permute(0, 3, 1, 2).double()
+    u = F.group_norm(xr, 32, gamma.double(), beta.double(), eps=1e-6)
+    want = F.conv2d(u * torch.sigmoid(u), w.to(cuda).double(), b.double(), padding=1)
+    got = fused if nchw else fused.permute(0, 3, 1, 2)
+    if residual:
+        want = want + res.permute(0, 3, 1, 2).double()
+    assert _rel(got, want) < (3e-5 if terms == 2 else 4e-3)
+
+
+def test_pipeline_identical_with_and_without_fused_gn(cuda):
+    """the whole encode -> quantize -> decode at BASELINE config 1's size: fused and two-launch forms give the same
+    indices and the same pixels bit for bit (GroupNorm statistics are fp64 atomics: compared to rounding)"""
+    import contextlib
+    import io
+    from text2human_b200 import ops
+    from text2human_b200.pipeline import VQImageSegmTextureModel
+    ops.set_precision("fp32")
+    opt = dict(embed_dim=256, n_embed=1024, double_z=False, z_channels=256, resolution=512, in_channels=3,
+               out_ch=3, ch=128, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2, attn_resolutions=[32], dropout=0.0)
+    torch.manual_seed(2021)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = VQImageSegmTextureModel(opt)
+    cb = R.codebooks(7, 18, 1024, 256, "trained")
+    for k, e in enumerate(m.quantize.embedding_list):
+        e.weight.data.copy_(cb[k])
+    m = m.to(cuda).eval()
+    x = R.image(2021, 2, 3, 256, 128).to(cuda)
+    mask = R.blocky_mask(2021, 2, 256, 128, 32).to(cuda)
+    old = ops.set_fuse_gn(True)
+    try:
+        l0 = ops.COUNTERS["launches"]
+        dec_f, _, info_f = m.forward_step(x, mask, return_info=True)
+        n_fused = ops.COUNTERS["launches"] - l0
+        ops.set_fuse_gn(False)
+        l0 = ops.COUNTERS["launches"]
+        dec_p, _, info_p = m.forward_step(x, mask, return_info=True)
+        n_plain = ops.COUNTERS["launches"] - l0
+    finally:
+        ops.set_fuse_gn(old)
+    print(f"[fused gn] libt2h launches per step: {n_fused} fused vs {n_plain} two-launch")
+    assert n_fused < n_plain - 30
+    assert torch.equal(info_f["idx_cont"], info_p["idx_cont"])
+    assert _rel(dec_f, dec_p) < 1e-6

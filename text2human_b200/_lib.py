@@ -42,6 +42,8 @@ class TapGemmParams(C.Structure):
         ("gn_stats", C.c_void_p), ("gn_cpg", C.c_int32), ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("bias_sn", C.c_int64), ("k_split", C.c_int32),
         ("use_tap_w", C.c_int32), ("tap_w", C.c_int32 * MAX_TAPS), ("accumulate", C.c_int32),
         ("k_partials", C.c_int32), ("d_slab", C.c_int64),
+        ("a_f32", C.c_void_p), ("a_gn_stats", C.c_void_p), ("a_gn_gamma", C.c_void_p), ("a_gn_beta", C.c_void_p),
+        ("a_gn_eps", C.c_float), ("a_gn_swish", C.c_int32), ("a_gn_groups", C.c_int32),
     ]
 
 

@@ -62,6 +62,13 @@ struct TapGemmDev {
   int wg, accum;
   int wg_pair, wg_ntaps;  // wg_pair: one 128 x 256 tile holds TWO taps side by side (Cin <= 128: N = 256 MMAs run at
                           // the full tensor rate, N = 128 at half of it); image index = tap pair
+  // fused GroupNorm(+swish) activation producer (tapgemm_swap_kernel<MBLK, true>): fp32 NHWC source + statistics
+  const float* ax;
+  long long ax_sn, ax_sh, ax_sw;
+  const double* ag_stats;
+  const float *ag_gamma, *ag_beta;
+  float ag_eps;
+  int ag_swish, ag_groups, ag_hw, ag_H, ag_W;
   int partials;  // split-K without reduction: k-slice s of a tile is stored to image slot t.img + s of D
   int wg_PW, wg_PH, wg_pw, wg_ppi;
   int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
@@ -843,7 +850,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return T2H_OK;
 }
 
-template <int MBLK>
+template <int MBLK, bool FUSE>
 static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                        const CUtensorMap& tmR, const TapGemmDev& P, cudaStream_t stream) {
   using C = Cfg<128, MBLK>;
@@ -851,7 +858,7 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int dev = 0;
   T2H_CUDA(cudaGetDevice(&dev));
   if (!configured[dev & 63]) {
-    T2H_CUDA(cudaFuncSetAttribute(tapgemm_swap_kernel<MBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    T2H_CUDA(cudaFuncSetAttribute(tapgemm_swap_kernel<MBLK, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   kDynSmem));
     configured[dev & 63] = true;
   }
@@ -868,7 +875,7 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int nb = (kRingBytes - Q.a_slots * C::kASlot) / C::kBSlot;
   Q.b_slots = nb > kMaxSlots ? kMaxSlots : nb;
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
-  T2H_CUDA(launch_pdl(tapgemm_swap_kernel<MBLK>, dim3(grid), dim3(kSwapThreads), kDynSmem, stream, 1, tmA, tmB,
+  T2H_CUDA(launch_pdl(tapgemm_swap_kernel<MBLK, FUSE>, dim3(grid), dim3(kSwapThreads), kDynSmem, stream, 1, tmA, tmB,
                       tmD, tmR, Q));
   return T2H_OK;
 }
@@ -884,13 +891,13 @@ extern "C" int t2h_debug_read(long long* out, int n) {
 }
 
 extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
-  T2H_CHECK_ARG(p && p->a && p->b && p->d, "tapgemm: null operand");
+  T2H_CHECK_ARG(p && (p->a || p->a_f32) && p->b && p->d, "tapgemm: null operand");
   T2H_CHECK_ARG(p->n_img > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->n_out > 0,
                 "tapgemm: empty problem (n_img=%d H=%d W=%d C=%d n_out=%d)", p->n_img, p->H, p->W, p->C,
                 p->n_out);
   T2H_CHECK_ARG(p->ntaps >= 1 && p->ntaps <= T2H_MAX_TAPS, "tapgemm: ntaps=%d", p->ntaps);
   T2H_CHECK_ARG(p->nterms == 1 || p->nterms == 3, "tapgemm: nterms must be 1 or 3 (got %d)", p->nterms);
-  T2H_CHECK_ARG(p->nterms == 1 || (p->a_terms == 2 && p->b_terms == 2),
+  T2H_CHECK_ARG(p->nterms == 1 || ((p->a_terms == 2 || p->a_f32) && p->b_terms == 2),
                 "tapgemm: nterms=3 needs hi/lo planes on both operands");
   T2H_CHECK_ARG(p->d_mode == T2H_OUT_F32 || p->d_mode == T2H_OUT_PLANES, "tapgemm: d_mode=%d", p->d_mode);
   T2H_CHECK_ARG(p->d_mode == T2H_OUT_F32 || p->d_terms == 1 || p->d_terms == 2, "tapgemm: d_terms=%d",
@@ -946,6 +953,19 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
       no_swap = e ? atoi(e) : 0;
     }
     if (no_swap) swap = false;
+  }
+  if (p->a_f32) {
+    // fused GroupNorm(+swish) producer: only in the swapped kernel, whole 64-channel chunks, table of <= 256 channels
+    bool ok = swap && p->C % 64 == 0 && p->C <= 256 && p->a_gn_stats && p->a_gn_gamma && p->a_gn_beta &&
+              p->a_gn_groups > 0 && p->C % p->a_gn_groups == 0 && !p->a_bcast &&
+              reinterpret_cast<uintptr_t>(p->a_f32) % 16 == 0 && p->a_sw % 4 == 0 && p->a_sh % 4 == 0 && p->a_sn % 4 == 0;
+    for (int i = 0; i < p->ntaps; ++i) ok = ok && p->tap_img_off[i] == 0;
+    T2H_CHECK_ARG(ok, "tapgemm: the fused GroupNorm producer needs a swapped-kernel conv (Cout %% 128 == 0 or a strided "
+                      "small-Cout output), C %% 64 == 0, C <= 256 and aligned fp32 NHWC input (C=%d n_out=%d)", p->C, p->n_out);
+    P.ax = p->a_f32; P.ax_sn = p->a_sn; P.ax_sh = p->a_sh; P.ax_sw = p->a_sw;
+    P.ag_stats = p->a_gn_stats; P.ag_gamma = p->a_gn_gamma; P.ag_beta = p->a_gn_beta; P.ag_eps = p->a_gn_eps;
+    P.ag_swish = p->a_gn_swish; P.ag_groups = p->a_gn_groups; P.ag_hw = p->a_H * p->a_W;
+    P.ag_H = p->a_H; P.ag_W = p->a_W;
   }
   if (p->a_mn || p->b_mn) {
     T2H_CHECK_ARG(rows_mode && p->ntaps == 1 && p->tap_dx[0] == 0 && p->tap_dy[0] == 0,
@@ -1081,7 +1101,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
 
   // ---- tensor maps
   CUtensorMap tmA, tmB, tmD, tmR;
-  {
+  if (!p->a_f32) {
     uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)p->a_W, (uint64_t)p->a_H, (uint64_t)p->a_imgs};
     uint64_t str[4] = {1, (uint64_t)p->a_sw, (uint64_t)p->a_sh, (uint64_t)p->a_sn};
     uint32_t box[4] = {(uint32_t)kBK, (uint32_t)TW, (uint32_t)P.slab_rows, 1};
@@ -1105,6 +1125,7 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     int rc = make_tmap(&tmB, p->b, 2, 4, dims, str, box, "tapgemm B");
     if (rc) return rc;
   }
+  if (p->a_f32) tmA = tmB;  // unused by the fused-producer kernel
   tmD = tmA;
   tmR = tmA;
   if (P.epi_mode != EPI_DIRECT) {
@@ -1136,7 +1157,9 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   }
 
   cudaStream_t s = as_stream(stream);
-  if (swap) return MBLK == 2 ? launch_swap<2>(tmA, tmB, tmD, tmR, P, s) : launch_swap<1>(tmA, tmB, tmD, tmR, P, s);
+  if (swap && p->a_f32)
+    return MBLK == 2 ? launch_swap<2, true>(tmA, tmB, tmD, tmR, P, s) : launch_swap<1, true>(tmA, tmB, tmD, tmR, P, s);
+  if (swap) return MBLK == 2 ? launch_swap<2, false>(tmA, tmB, tmD, tmR, P, s) : launch_swap<1, false>(tmA, tmB, tmD, tmR, P, s);
   if (MBLK == 2) return launch<128, 2>(tmA, tmB, tmD, tmR, P, s);
   switch (BN) {
     case 16: return launch<16, 1>(tmA, tmB, tmD, tmR, P, s);

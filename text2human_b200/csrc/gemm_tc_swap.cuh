@@ -21,13 +21,20 @@ constexpr int kWarpTile = 32 * 128;  // 32 pixels x 32 fp32 channels
 
 constexpr int kSwapThreads = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 
-template <int MBLK>
+// FUSE = true: the activation operand is NOT read as fp16 planes by TMA.  The kernel takes the fp32 NHWC tensor the
+// previous conv wrote plus its GroupNorm statistics, and four producer warps (8-11, taken from the epilogue's eight)
+// build the swizzled hi / lo slabs the MMAs read themselves: 128-bit loads -> (x - mean) * rstd * gamma + beta ->
+// swish -> fp16 split -> st.shared in the 128-byte-swizzle image a TMA box would have produced.  This is
+// Normalize() + nonlinearity() (vqgan_arch.py:510-517) folded into the consuming conv: the gn_apply pass and its
+// 8 bytes per element of HBM traffic disappear.  Same arithmetic, same order as gn_apply_kernel -> identical slabs.
+template <int MBLK, bool FUSE>
 __global__ void __launch_bounds__(kSwapThreads, 1)
 tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                     const __grid_constant__ TapGemmDev P) {
   using C = Cfg<128, MBLK>;
   constexpr int NPIX = MBLK * 128;  // pixels per tile = UMMA N
+  constexpr int EW = FUSE ? 4 : 8;   // epilogue warps
   pdl_launch_dependents();  // the next kernel may start its prologue once every CTA of this one is running
   const int NA = P.a_slots, NB = P.b_slots;
   extern __shared__ uint8_t smem_raw[];
@@ -46,12 +53,13 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ __align__(8) uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float gn_tab[FUSE ? 512 : 1];  // FUSE: per-channel scale | shift of the current image (C <= 256)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
+    if (!FUSE) tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (P.epi_mode != EPI_DIRECT) tma_prefetch_desc(&tmD);
     if (P.residual) tma_prefetch_desc(&tmR);
@@ -67,7 +75,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], EW);
     }
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_mbar_init();
@@ -87,7 +95,89 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int a_planes = (P.nterms == 3) ? 2 : 1;
   const int slab_bytes = P.slab_rows * P.TW * 128;
 
-  if (warp == 0) {
+  if (FUSE && warp >= 8) {
+    // ---------------------------------------------- activation slab producers: GroupNorm + swish + fp16 split
+    const int pt = threadIdx.x - 256;  // 0..127
+    float* s_scale = gn_tab;
+    float* s_shift = gn_tab + 256;
+    const int tw_shift = 31 - __clz(P.TW);
+    const int R = P.slab_rows * P.TW;  // pixels of one slab
+    const int units = R * 8;           // 8 channels (one 16-byte smem chunk) each
+    const int cpg = P.C / P.ag_groups;
+    const double cnt = (double)P.ag_hw * cpg;
+    int cur_img = -1;
+    int sa = 0, pa = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile, MBLK, 128);
+      if (t.img != cur_img) {
+        named_bar_sync(3, 128);  // nobody still reads the previous image's table
+        for (int c = pt; c < P.C; c += 128) {
+          const int g = c / cpg;
+          const double su = P.ag_stats[((long long)t.img * P.ag_groups + g) * 2 + 0];
+          const double sq = P.ag_stats[((long long)t.img * P.ag_groups + g) * 2 + 1];
+          const double mean = su / cnt;
+          double var = sq / cnt - mean * mean;
+          if (var < 0) var = 0;
+          const float rstd = (float)(1.0 / sqrt(var + (double)P.ag_eps));
+          const float ga = P.ag_gamma[c] * rstd;
+          s_scale[c] = ga;
+          s_shift[c] = P.ag_beta[c] - (float)mean * ga;
+        }
+        named_bar_sync(3, 128);
+        cur_img = t.img;
+      }
+      const float* ximg = P.ax + (long long)t.img * P.ax_sn;
+      for (int g = 0; g < P.ngroups; ++g) {
+        const int h_base = t.h0 + P.g_dy0[g], w_base = t.w0 + P.g_dx[g];
+        for (int ch = 0; ch < P.kchunks; ++ch) {
+          const int s_hi = sa;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+          int s_lo = -1;
+          if (a_planes == 2) {
+            s_lo = sa;
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            if (++sa == NA) { sa = 0; pa ^= 1; }
+          }
+          uint8_t* hi_base = a_ring + s_hi * C::kASlot;
+          uint8_t* lo_base = a_ring + (s_lo >= 0 ? s_lo : s_hi) * C::kASlot;
+          const int c0 = ch * kBK;
+#pragma unroll 4
+          for (int u = pt; u < units; u += 128) {
+            const int r = u >> 3, j = u & 7;
+            const int h = h_base + (r >> tw_shift), w = w_base + (r & (P.TW - 1));
+            const bool ok = (h >= 0) && (h < P.ag_H) && (w >= 0) && (w < P.ag_W);
+            const float* src = ximg + (long long)h * P.ax_sh + (long long)w * P.ax_sw + c0 + j * 8;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (ok) {
+              v0 = __ldg(reinterpret_cast<const float4*>(src));
+              v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            }
+            const float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            __align__(16) __half hh[8];
+            __align__(16) __half ll[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float y = 0.f;
+              if (ok) {   // conv zero padding applies to the NORMALISED activation: outside pixels stay 0
+                y = f[e] * s_scale[c0 + j * 8 + e] + s_shift[c0 + j * 8 + e];
+                if (P.ag_swish) y = y / (1.0f + __expf(-y));
+              }
+              split_f16(y, hh[e], ll[e]);
+            }
+            *reinterpret_cast<uint4*>(hi_base + swz(r, j)) = *reinterpret_cast<const uint4*>(hh);
+            if (s_lo >= 0) *reinterpret_cast<uint4*>(lo_base + swz(r, j)) = *reinterpret_cast<const uint4*>(ll);
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+          named_bar_sync(3, 128);
+          if (pt == 0) {
+            mbar_arrive(&a_full[s_hi]);
+            if (s_lo >= 0) mbar_arrive(&a_full[s_lo]);
+          }
+        }
+      }
+    }
+  } else if (!FUSE && warp == 0) {
     // ---------------------------------------------- activation slab producer
     if (lane == 0 && !(P.debug & 8)) {
       int sa = 0, pa = 0;
@@ -224,7 +314,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         g_t2h_dbg[blockIdx.x * 4 + 3] = t_exec;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + EW) {
     // ---------------------------------------------- per-warp transposed epilogue
     // Two warps per TMEM lane quadrant take alternate 32-pixel chunks, so one warp's TMEM/TMA
     // latencies hide behind the other's arithmetic.  Each warp owns one 4 KB output tile and one
@@ -253,17 +343,18 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_load_4d(&tmR, &res_bar[e], my_res, c0, t.w0, t.h0 + k * rows_per_chunk, t.img);
       };
       if (has_res && lane == 0) issue_res(half);
+      constexpr int KSTEP = EW / 4;  // chunks are dealt round-robin to the quadrant's warps
       // interior tiles need no per-pixel validity test for the GroupNorm sums
       const bool interior = (t.h0 + MBLK * P.TH <= P.H) && (t.w0 + P.TW <= P.W);
       float gs = 0.f, gss = 0.f;
       mbar_wait(&tfull_bar[as], ap);
       tc_fence_after();
 #pragma unroll 1
-      for (int k = half; k < NCH; k += 2) {
+      for (int k = half; k < NCH; k += KSTEP) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + k * 32, r);
         tmem_ld_wait();
-        if (k + 2 >= NCH) {
+        if (k + KSTEP >= NCH) {
           // this warp's last TMEM read of the accumulator
           tc_fence_before();
           __syncwarp();
@@ -274,7 +365,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&res_bar[e], res_par);
             res_par ^= 1;
             __syncwarp();
-            if (lane == 0 && k + 2 < NCH) issue_res(k + 2);
+            if (lane == 0 && k + KSTEP < NCH) issue_res(k + KSTEP);
           }
           continue;
         }
@@ -298,7 +389,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
             v[i] += *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
           __syncwarp();
-          if (lane == 0 && k + 2 < NCH) issue_res(k + 2);  // overlaps the rest of this chunk
+          if (lane == 0 && k + KSTEP < NCH) issue_res(k + KSTEP);  // overlaps the rest of this chunk
         }
         if (P.gn_stats) {
           if (interior) {

@@ -81,6 +81,22 @@ def Normalize(in_channels):
     return torch.nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
 
 
+def _gn_conv3x3(act, norm, conv, *, residual=None, want_stats=False, nchw_out=False):
+    """swish(GroupNorm(act)) -> 3x3 conv: one fused launch where the kernel supports it (the normalisation happens
+    in the conv's activation producer), else the gn_apply pass followed by the conv"""
+    x = act.x
+    N, H, W, Cc = x.shape
+    Cout = conv.weight.shape[0]
+    if norm.num_groups == ops.GN_GROUPS and ops.can_fuse_gn(Cc, Cout, W, norm.num_groups, nchw_out=nchw_out):
+        stats = act.stats if act.stats is not None else ops.norm_stats(x, norm.num_groups)
+        return ops.conv3x3_gn(x, stats, _f32(norm.weight), _f32(norm.bias), _conv_w(conv), _f32(conv.bias),
+                              eps=norm.eps, swish=True, groups=norm.num_groups, residual=residual,
+                              nchw_out=nchw_out, want_stats=want_stats)
+    a = _gn(act, norm, swish=True, consumer=conv)
+    return ops.conv3x3(a, _conv_w(conv), _f32(conv.bias), residual=residual, nchw_out=nchw_out,
+                       want_stats=want_stats)
+
+
 def _gn(act, norm, swish, consumer=None):
     """``consumer``: the conv that reads the planes (decides how many planes are written)"""
     stats = act.stats if norm.num_groups == ops.GN_GROUPS else None
@@ -166,10 +182,8 @@ class ResnetBlock(nn.Module):
     def _fwd(self, act):
         assert self.dropout.p == 0.0 or not self.training, "dropout>0 in training is not implemented"
         x = act.x
-        a = _gn(act, self.norm1, swish=True, consumer=self.conv1)
         # conv1's epilogue accumulates the statistics norm2 needs
-        h = _Act(*ops.conv3x3(a, _conv_w(self.conv1), _f32(self.conv1.bias), want_stats=True))
-        a = _gn(h, self.norm2, swish=True, consumer=self.conv2)
+        h = _Act(*_gn_conv3x3(act, self.norm1, self.conv1, want_stats=True))
         if self.in_channels != self.out_channels:
             xp = ops.f32_to_planes(x, CVT_PLAIN)
             if self.use_conv_shortcut:
@@ -177,7 +191,7 @@ class ResnetBlock(nn.Module):
             else:
                 x = conv1x1_nhwc(None, self.nin_shortcut, planes_in=xp)
         # residual add (and the next GroupNorm's statistics) fused into conv2's epilogue
-        return _Act(*ops.conv3x3(a, _conv_w(self.conv2), _f32(self.conv2.bias), residual=x, want_stats=True))
+        return _Act(*_gn_conv3x3(h, self.norm2, self.conv2, residual=x, want_stats=True))
 
     def forward_nhwc(self, x, temb=None):
         assert temb is None, "temb is always None on the Text2Human path (temb_ch=0)"
@@ -247,8 +261,7 @@ def _conv_in_nhwc(conv, x):
 
 
 def _conv_out(norm, conv, act, nchw):
-    a = _gn(act, norm, swish=True)
-    return ops.conv3x3(a, _conv_w(conv), _f32(conv.bias), nchw_out=nchw)
+    return _gn_conv3x3(act, norm, conv, nchw_out=nchw)
 
 
 class Encoder(nn.Module):
