@@ -506,6 +506,39 @@ def gpu_eager_baseline(dev, batch=16, steps=3):
                                                         note="the reference's unmodified sample_fn loop, 8 steps, wall clock")
             del net
             torch.cuda.empty_cache()
+            # config 5: the reference's own VQImageSegmTextureModel.optimize_parameters (vqgan_model.py:329-344,
+            # :444-488; LPIPS stubbed to zero exactly as on our arm), stock PyTorch autograd + torch.optim.Adam,
+            # batch 8 (= our micro-batch) at 512x256.  "default" = the reference as shipped: cuDNN convs may use TF32
+            # (PyTorch's default), matmuls fp32; bf16_autocast wraps the unmodified step in torch.autocast.
+            ns3 = RL.install("reference", wrappers=("vqgan_model",))
+            opt = dict(VQVAE_TOP, n_channels=3, ndf=64, disc_layers=3, perceptual_weight=1.0, disc_start_step=0,
+                       disc_weight_max=1.0, diff_aug=True, lr=1e-4)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):
+                wr = ns3.vqgan_model.VQImageSegmTextureModel(opt)
+            tb = 8
+            data = dict(image=R.image(300, tb, 3, 512, 256), texture_mask=R.blocky_mask(300, tb, 512, 256, 32))
+            for name, mm_tf32, cudnn_tf32, cast in (("fp32", False, False, False), ("default", False, True, False),
+                                                    ("tf32", True, True, False), ("bf16_autocast", True, True, True)):
+                try:
+                    torch.backends.cuda.matmul.allow_tf32 = mm_tf32
+                    torch.backends.cudnn.allow_tf32 = cudnn_tf32
+                    ctx = torch.autocast("cuda", dtype=torch.bfloat16) if cast else contextlib.nullcontext()
+                    with ctx:
+                        wr.optimize_parameters(data, 2)
+                        torch.cuda.synchronize()
+                        e0.record()
+                        for i in range(2):
+                            wr.optimize_parameters(data, 3 + i)
+                        e1.record()
+                        torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / 2
+                    out[f"config5_train_{name}"] = dict(img_per_s=tb / (ms / 1e3), ms_per_step=ms, batch=tb,
+                                                        note="reference optimize_parameters, unmodified, one GPU")
+                except Exception as exc:
+                    out[f"config5_train_{name}"] = dict(error=repr(exc))
+            del wr
+            torch.cuda.empty_cache()
     except Exception as exc:
         out["error"] = repr(exc)
     finally:

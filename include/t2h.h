@@ -222,6 +222,18 @@ int t2h_add_inplace(float* x, const float* y, int64_t numel, t2h_stream_t stream
 int t2h_softmax_rows(const float* s, void* out, int64_t rows, int cols, float scale,
                      int terms, t2h_stream_t stream);
 
+/* Multi-head attention of the index-prediction transformer as one kernel: out = softmax(q k^T * scale) v per
+ * (sequence, head) -- CausalSelfAttention.forward with causal=False, transformer_arch.py:41-67 (the k/q/v
+ * .view().transpose(1, 2) head splits, `att = q @ k^T * (1/sqrt(hs))`, F.softmax, `att @ v`, the transpose back).
+ * qkv: fp16 planes [terms][rows][ld] (hi [, lo]; `plane` elements apart) holding q, k, v of head h in columns
+ * q_col / k_col / v_col + 64 h (e.g. the fused q|k|v projection); rows >= batch * tokens, sequence s = rows
+ * s*tokens ..; out: fp16 planes [terms][rows][ld_out], heads side by side.  head_dim must be 64 and tokens a
+ * multiple of 128 in 128..512 (the score rows of a query block live in tensor memory) -- other shapes take
+ * t2h_tapgemm (q k^T), t2h_softmax_rows, t2h_tapgemm (p v). */
+int t2h_attn_fwd(const void* qkv, int terms, int64_t plane, int64_t ld, int64_t rows, int q_col, int k_col,
+                 int v_col, int batch, int tokens, int heads, int head_dim, float scale, void* out,
+                 int64_t out_plane, int64_t ld_out, t2h_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Codebook quantizers (fp32 CUDA-core math, bit-reproducible; see
  * oracle/vq_oracle.c for the exact operation order)

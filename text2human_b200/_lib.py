@@ -79,6 +79,7 @@ SIGNATURES = {
     "t2h_gn_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P]),
     "t2h_add_inplace": (_I, [_P, _P, _L, _P]),
     "t2h_softmax_rows": (_I, [_P, _P, _L, _I, _F, _I, _P]),
+    "t2h_attn_fwd": (_I, [_P, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _F, _P, _L, _L, _P]),
     "t2h_vq_search": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P,
                            _P, _L, _P]),
     "t2h_vq_workspace_bytes": (_L, [_L, _I, _I]),

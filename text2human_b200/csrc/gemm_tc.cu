@@ -1268,3 +1268,5 @@ extern "C" int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t strea
     default: return launch<256, 1>(tmA, tmB, tmD, tmR, P, s);
   }
 }
+
+#include "attn_fused.cuh"

@@ -705,6 +705,38 @@ def softmax_rows(s, scale=1.0, terms=None):
     return out
 
 
+# Multi-head attention as one kernel (csrc/attn_fused.cuh) where its shape constraints hold; T2H_FUSED_ATTN=0 (or
+# set_fused_attn(False)) keeps the three-launch q k^T / softmax / p v path for A/B measurements.
+FUSED_ATTN = {"on": _os_env.environ.get("T2H_FUSED_ATTN", "1") != "0"}
+
+
+def set_fused_attn(on):
+    old = FUSED_ATTN["on"]
+    FUSED_ATTN["on"] = bool(on)
+    return old
+
+
+def can_fuse_attn(tokens, head_dim):
+    return FUSED_ATTN["on"] and head_dim == 64 and tokens % 128 == 0 and 128 <= tokens <= 512
+
+
+def attn_fused(qkv, B, Tn, nh, scale, out=None):
+    """softmax(q k^T * scale) v per (sequence, head) in one launch (transformer_arch.py:41-67).
+    qkv: planes [T, B*Tn, 3C], the fused q | k | v projection with the heads side by side (C = nh * 64).
+    -> planes [T, B*Tn, C]."""
+    _need_cuda(qkv)
+    T, M, C3 = qkv.shape
+    Cc = C3 // 3
+    assert M == B * Tn and Cc == nh * 64 and qkv.stride(2) == 1 and qkv.dtype == torch.float16
+    if out is None:
+        out = torch.empty((T, M, Cc), dtype=torch.float16, device=qkv.device)
+    assert out.shape == (T, M, Cc) and out.stride(2) == 1
+    _count(1)
+    _lib.check(_lib.load().t2h_attn_fwd(_ptr(qkv), T, qkv.stride(0), qkv.stride(1), M, 0, Cc, 2 * Cc, B, Tn, nh, 64,
+                                        float(scale), _ptr(out), out.stride(0), out.stride(1), _stream()))
+    return out
+
+
 def layer_norm(x, gamma, beta, eps=1e-5, terms=None):
     """LayerNorm over the last dim of fp32 [rows, C] -> planes [T, rows, C]."""
     _need_cuda(x)

@@ -69,6 +69,8 @@ class CausalSelfAttention(nn.Module):
         nh = self.n_head
         wqkv, bqkv = self._qkv_packed()
         qkv = ops.linear(hn, wqkv, bqkv, planes_out=True)  # [Tt, M, 3C]  (q | k | v), heads side by side
+        if ops.can_fuse_attn(T, Cc // nh):
+            return _linear_residual(ops.attn_fused(qkv, B, T, nh, 1.0 / math.sqrt(Cc // nh)), self.proj, x_res)
         s = ops.mha_scores(qkv[:, :, :Cc], B, T, nh, k=qkv[:, :, Cc:2 * Cc])  # fp32 [B, nh, T, T]
         p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // nh))  # planes [Tt, B, nh, T, T]
         # v stays token-major inside qkv: the tensor core reads it as an MN-major operand (no v^T copy)
@@ -112,9 +114,12 @@ class Block(nn.Module):
         Tt, M, Cc = h.shape
         wqkv, bqkv = a._qkv_packed()
         qkv = ops.linear(h, wqkv, bqkv, planes_out=True)
-        s = ops.mha_scores(qkv[:, :, :Cc], B, T, a.n_head, k=qkv[:, :, Cc:2 * Cc])
-        p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // a.n_head))
-        y = ops.mha_pv(p, qkv[:, :, 2 * Cc:], B, T, a.n_head, v_tok=True)
+        if ops.can_fuse_attn(T, Cc // a.n_head):
+            y = ops.attn_fused(qkv, B, T, a.n_head, 1.0 / math.sqrt(Cc // a.n_head))
+        else:
+            s = ops.mha_scores(qkv[:, :, :Cc], B, T, a.n_head, k=qkv[:, :, Cc:2 * Cc])
+            p = ops.softmax_rows(s, scale=1.0 / math.sqrt(Cc // a.n_head))
+            y = ops.mha_pv(p, qkv[:, :, 2 * Cc:], B, T, a.n_head, v_tok=True)
         part = ops.linear_partials(y, _lin_w(a.proj), ks)
         x, h2 = ops.splitk_reduce_ln(part, _f32(a.proj.bias), x, _f32(self.ln2.weight), _f32(self.ln2.bias), self.ln2.eps)
         m = ops.linear(h2, _lin_w(self.mlp[0]), _f32(self.mlp[0].bias), planes_out=True, act=ops.ACT_GELU)
