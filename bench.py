@@ -163,33 +163,21 @@ def side_workloads(dev, precision):
         gen = torch.Generator(device=dev).manual_seed(2021)
         sm.sample_fn(segm, tm, sample_steps=4, generator=gen)
         torch.cuda.synchronize()
-        steps = 32
+        steps = SAMPLER_OPT["sample_steps"]               # the full 256-step sample of BASELINE config 4
         e0.record()
         sm.sample_fn(segm, tm, sample_steps=steps, generator=gen)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         out["config4_sampler"] = dict(batch=4, ms_per_diffusion_step=ms, measured_steps=steps,
-                                      tokens_per_s_256_steps=2048 / (ms * 256 / 1e3), extrapolated=True,
+                                      tokens_per_s_256_steps=2048 / (ms * 256 / 1e3), extrapolated=False,
                                       algorithmic_tflops=4 * 99.86 / ms, precision=precision,
-                                      launch="CUDA graph replay of the transformer forward per step")
-        # opt-in small-batch mode: proj / fc2 split over the contraction and reduce-added into the residual
-        # stream (fp32 summation order then varies run to run, so it is not the default)
-        old_sk = ops.set_split_k(inference=True)
-        try:
-            sm._graphs.clear()
-            sm.sample_fn(segm, tm, sample_steps=4, generator=gen)
-            torch.cuda.synchronize()
-            e0.record()
-            sm.sample_fn(segm, tm, sample_steps=steps, generator=gen)
-            e1.record()
-            torch.cuda.synchronize()
-            ms_sk = e0.elapsed_time(e1) / steps
-            out["config4_sampler"]["split_k_opt_in"] = dict(ms_per_diffusion_step=ms_sk,
-                                                            tokens_per_s_256_steps=2048 / (ms_sk * 256 / 1e3))
-        finally:
-            ops.set_split_k(**old_sk)
-            sm._graphs.clear()
+                                      launch="CUDA graph replay of the transformer forward per step; fused attention "
+                                             "kernel (t2h_attn_fwd), deterministic split-K + fused reduce/LayerNorm",
+                                      launches_per_step=None)
+        l0 = ops.COUNTERS["launches"]
+        sm.sample_fn(segm, tm, sample_steps=2, generator=gen, use_graph=False)
+        out["config4_sampler"]["launches_per_step"] = (ops.COUNTERS["launches"] - l0) // 2
         # the refine half of sample_and_refine: sampled top tokens -> top codebook gather -> UNet/FCN
         # index prediction -> bottom gather -> DecoderRes -> Decoder, batched (the reference decodes one by one)
         del sm
