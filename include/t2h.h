@@ -167,7 +167,10 @@ typedef struct t2h_tapgemm_params {
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
-/* profiling aid: copies the per-CTA counters the kernels record when T2H_DEBUG has bit 16 set */
+/* profiling aid: with T2H_DEBUG bit 16 set, CTA 0 of every tap-GEMM / fused-attention launch appends a record of 8
+ * words to a device ring: globaltimer ns at {entry, dependency wait passed, first operands landed, last MMA issued,
+ * accumulator complete, CTA done}, {work items, contraction chunks per item | kind << 32}.  out[0] = records so far,
+ * out[1..] = the ring (synchronises the device). */
 int t2h_debug_read(long long* out, int n);
 
 /* ------------------------------------------------------------------------

@@ -26,6 +26,7 @@ struct AttnDev {
   int terms;                            // 1: single fp16 plane, 2: hi + lo planes (3 tensor-core products)
   int q_col, k_col, v_col;
   float kfac;  // scale * log2(e)
+  int debug;   // T2H_DEBUG (bit 16: timeline record, see g_t2h_dbg)
   __half* out;
   long long out_plane, ld_out;
 };
@@ -59,7 +60,17 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmX);
+  __shared__ unsigned long long* trace_s;
+  if (warp == 0 && lane == 0) {
+    trace_s = nullptr;
+    if ((P.debug & 16) && blockIdx.x == 0) {
+      trace_s = g_t2h_dbg + (size_t)(atomicAdd(&g_t2h_dbg_n, 1u) % kTraceRecords) * 8;
+      trace_s[0] = gtime_ns();
+      trace_s[6] = gridDim.x;
+      trace_s[7] = (1ull << 32) | (unsigned long long)P.nchunks;
+    }
+    tma_prefetch_desc(&tmX);
+  }
   if (warp == 1 && lane == 0) {
     for (int c = 0; c < 8; ++c) mbar_init(&kv_full[c], 1);
     mbar_init(&s_full, 1);
@@ -79,6 +90,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
+  unsigned long long* const trace = trace_s;
+  if (trace && threadIdx.x == 0) trace[1] = gtime_ns();
 
   const int qb = (int)blockIdx.x % P.qblocks;
   const int hb = (int)blockIdx.x / P.qblocks;
@@ -123,6 +136,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int nck = min(4, NC - 4 * hf);
       for (int c = 4 * hf; c < 4 * hf + nck; ++c) mbar_wait(&kv_full[c], 0);
       tc_fence_after();
+      if (trace && lane == 0 && hf == 0) trace[2] = gtime_ns();
       if (elect_one()) {
         const uint32_t idesc = umma_idesc_f16(128, 64 * nck);
         const uint32_t d = tmem_base + hf * 256;
@@ -165,6 +179,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     if (elect_one()) umma_commit(&o_full);
     __syncwarp();
+    if (trace && lane == 0) trace[3] = gtime_ns();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + output, one query row per thread
     const int q = warp & 3;  // TMEM lane quarter of this warp
@@ -213,6 +228,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     mbar_wait(&o_full, 0);
     tc_fence_after();
+    if (trace && threadIdx.x == 128) trace[4] = gtime_ns();
     const float inv = 1.0f / sum;
     __half* ohi = P.out + (long long)(qrow0 + row) * P.ld_out + head * 64;
 #pragma unroll
@@ -230,6 +246,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (T2 == 2) *reinterpret_cast<uint4*>(ohi + P.out_plane + half * 32 + g * 8) = *reinterpret_cast<uint4*>(lo);
       }
     }
+    if (trace && threadIdx.x == 128) trace[5] = gtime_ns();
   }
 
   tc_fence_before();
@@ -285,6 +302,14 @@ extern "C" int t2h_attn_fwd(const void* qkv, int terms, int64_t plane, int64_t l
   P.out = reinterpret_cast<__half*>(out);
   P.out_plane = out_plane;
   P.ld_out = ld_out;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("T2H_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    P.debug = dbg;
+  }
   const int grid = batch * heads * P.qblocks;
   T2H_CUDA(launch_pdl(attn_fused_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmem, as_stream(stream), 1, tmX, P));
   T2H_LAUNCH_OK();

@@ -431,6 +431,97 @@ __global__ void splitk_reduce_ln_kernel(const float* __restrict__ part, int n_sl
   }
 }
 
+// The same pass for C % 4 == 0 with 128-bit accesses: lane l owns columns 4 (l + 32 i) .. +3.  Every load of a row is
+// issued before the first store (x_out may alias residual, so stores in the load loop would serialise it into
+// one L2 round trip per column group).  x_out is summed in the scalar kernel's order (bit-identical); the LayerNorm
+// statistics are reduced in a different, equally fixed, order.
+template <int VEC>
+__global__ void splitk_reduce_ln_vec_kernel(const float* __restrict__ part, int n_slabs, long long slab,
+                                            const float* __restrict__ bias, const float* residual, float* x_out,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                            __half* __restrict__ ln_out, int terms, long long plane,
+                                            const long long* __restrict__ row_map, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warps = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;
+  float4 v[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + i * 32;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < nv && residual) v[i] = *reinterpret_cast<const float4*>(residual + row * C + 4 * c4);
+  }
+  if (bias) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = lane + i * 32;
+      if (c4 < nv) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        v[i].x += b.x; v[i].y += b.y; v[i].z += b.z; v[i].w += b.w;
+      }
+    }
+  }
+  for (int s = 0; s < n_slabs; ++s) {
+    const float* ps = part + (long long)s * slab + row * C;
+    float4 p[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const int c4 = lane + i * 32;
+      p[i] = c4 < nv ? __ldg(reinterpret_cast<const float4*>(ps) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i].x += p[i].x; v[i].y += p[i].y; v[i].z += p[i].z; v[i].w += p[i].w;
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + i * 32;
+    if (c4 < nv) {
+      *reinterpret_cast<float4*>(x_out + row * C + 4 * c4) = v[i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  if (!ln_out) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + i * 32;
+    if (c4 < nv) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+  const long long orow = row_map ? row_map[row] : row;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int c4 = lane + i * 32;
+    if (c4 < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+      __align__(8) __half hi[4];
+      __align__(8) __half lo[4];
+      split_f16((v[i].x - mean) * rstd * g.x + b.x, hi[0], lo[0]);
+      split_f16((v[i].y - mean) * rstd * g.y + b.y, hi[1], lo[1]);
+      split_f16((v[i].z - mean) * rstd * g.z + b.z, hi[2], lo[2]);
+      split_f16((v[i].w - mean) * rstd * g.w + b.w, hi[3], lo[3]);
+      *reinterpret_cast<uint2*>(ln_out + orow * C + 4 * c4) = *reinterpret_cast<uint2*>(hi);
+      if (terms == 2) *reinterpret_cast<uint2*>(ln_out + plane + orow * C + 4 * c4) = *reinterpret_cast<uint2*>(lo);
+    }
+  }
+}
+
 // x[b,t,:] = tok[idx] + pos[t] + segm[sg] + tex[tx]
 __global__ void embed_sum_kernel(const long long* __restrict__ idx, const long long* __restrict__ segm,
                                  const long long* __restrict__ tex, const float* __restrict__ tok_emb,
@@ -743,7 +834,17 @@ int t2h_splitk_reduce_ln(const float* partials, int n_slabs, int64_t slab, const
   const long long plane = (long long)ln_rows * c;
   const long long* rm = reinterpret_cast<const long long*>(row_map);
   cudaStream_t st = as_stream(stream);
-  if (c <= 512)
+  const bool aligned = (c % 4 == 0) && (slab % 4 == 0) && ((reinterpret_cast<uintptr_t>(partials) | reinterpret_cast<uintptr_t>(x_out) |
+                                                           reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(bias) |
+                                                           reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(ln_out) % 8 == 0) && (plane % 4 == 0);
+  if (aligned && c <= 512)
+    T2H_CUDA(launch_pdl(splitk_reduce_ln_vec_kernel<4>, dim3(grid), dim3(warps * 32), 0, st, 1, partials, n_slabs,
+                        (long long)slab, bias, residual, x_out, gamma, beta, eps, o, terms, plane, rm, (long long)rows, c));
+  else if (aligned)
+    T2H_CUDA(launch_pdl(splitk_reduce_ln_vec_kernel<8>, dim3(grid), dim3(warps * 32), 0, st, 1, partials, n_slabs,
+                        (long long)slab, bias, residual, x_out, gamma, beta, eps, o, terms, plane, rm, (long long)rows, c));
+  else if (c <= 512)
     T2H_CUDA(launch_pdl(splitk_reduce_ln_kernel<16>, dim3(grid), dim3(warps * 32), 0, st, 1, partials, n_slabs,
                         (long long)slab, bias, residual, x_out, gamma, beta, eps, o, terms, plane, rm, (long long)rows, c));
   else

@@ -74,8 +74,17 @@ struct TapGemmDev {
   int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
 };
 
-// profiling scratch (T2H_DEBUG bit 16): per CTA {MMA-thread cycles, MMAs issued, epilogue-warp cycles, tiles}
-__device__ long long g_t2h_dbg[148 * 4];
+// profiling trace (T2H_DEBUG bit 16): CTA 0 of every tap-GEMM / attention launch appends one record of 8 words --
+// globaltimer (ns) at {kernel entry, griddepcontrol.wait passed, first operand tile landed, last MMA issued,
+// accumulator complete (epilogue woke), CTA done}, then {total work items, contraction chunks per item | kind << 32}
+constexpr int kTraceRecords = 2048;
+__device__ unsigned long long g_t2h_dbg[kTraceRecords * 8];
+__device__ unsigned int g_t2h_dbg_n;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 constexpr int kBK = 64;                      // fp16 elements per 128-byte swizzled row
 constexpr int kABlockBytes = 128 * 128;      // one 128-row A block of a stage
@@ -199,11 +208,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t res_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float gsum[2][2 * 128];  // GroupNorm partial sums of the current / previous tile
+  __shared__ __align__(16) float sbias[BN];  // column bias of the current tile (plane epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  __shared__ unsigned long long* trace_s;  // this launch's trace record (CTA 0, T2H_DEBUG bit 16), else null
 
   if (warp == 0 && lane == 0) {
+    trace_s = nullptr;
+    if ((P.debug & 16) && blockIdx.x == 0) {
+      trace_s = g_t2h_dbg + (size_t)(atomicAdd(&g_t2h_dbg_n, 1u) % kTraceRecords) * 8;
+      trace_s[0] = gtime_ns();
+      trace_s[6] = (unsigned long long)P.total_work;
+      trace_s[7] = (unsigned long long)min(P.kper, P.kchunks) * P.ngroups;
+    }
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (P.epi_mode != EPI_DIRECT) tma_prefetch_desc(&tmD);
@@ -238,6 +256,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // everything above touched only shared / tensor memory and kernel parameters; from here on the previous
   // kernel's results are read (and buffers it may still be reading are overwritten)
   pdl_wait();
+  unsigned long long* const trace = trace_s;
+  if (trace && threadIdx.x == 0) trace[1] = gtime_ns();
 
   const int a_planes = (P.nterms == 3) ? 2 : 1;  // slabs per (group, chunk): hi [, lo]
   const int slab_bytes = P.slab_rows * P.TW * 128;
@@ -409,6 +429,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             mbar_wait(&a_full[sa_hi], pa_hi);
             tc_fence_after();
+            if (trace && lane == 0 && work == work0 && g == 0 && ch == ch0) trace[2] = gtime_ns();
             const uint32_t ahi = a_lo0 + sa_hi * A16;
             const uint32_t alo = a_lo0 + sa_lo * A16;
             for (int tp = 0; tp < nt; ++tp) {
@@ -443,6 +464,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         { if (elect_one()) umma_commit(&tfull_bar[as]); __syncwarp(); }  // accumulator complete
+        if (trace && lane == 0 && work == work0) trace[3] = gtime_ns();
         if (++as == 2) {
           as = 0;
           ap ^= 1;
@@ -466,7 +488,75 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ch1 = min(P.kchunks, ch0 + P.kper);
       const TileCoord t = decode_tile(P, tile, MBLK, BN);
 
-      if (P.epi_mode == EPI_TMA_F32) {
+      bool plain_f32 = false;
+      if constexpr (BN >= 64) {
+        plain_f32 = P.epi_mode == EPI_TMA_F32 && !P.residual && !P.gn_stats && P.act == T2H_ACT_NONE && !P.wg_pair &&
+                    P.bias_mode != T2H_BIAS_ROW && !(P.debug & 1);
+      }
+      if (plain_f32) {
+        // ---- fp32 output with nothing but alpha / column bias in the epilogue (split-K slices, weight gradients,
+        // plain projections): 64-column units = two 32-column staging tiles, two pairs of them, so that a unit is
+        // converted while the previous unit's TMA stores still read theirs -- half the barrier rounds of the
+        // general path below
+        const int cols_left = P.n_out - t.n0;
+        const int nuc = (cols_left >= BN) ? BN / 64 : (cols_left + 63) / 64;
+        const int nunits = MBLK * nuc;
+        const bool add_bias = P.bias_mode == T2H_BIAS_COL && ch0 == 0;  // split-K: the first k-slice carries the bias
+        if (add_bias) {
+          for (int i = threadIdx.x - 128; i < BN; i += 128)
+            sbias[i] = (t.n0 + i < P.n_out) ? __ldg(P.bias + t.img * P.bias_sn + t.n0 + i) : 0.f;
+        }
+        mbar_wait(&tfull_bar[as], ap);
+        tc_fence_after();
+        if (trace && elected && work == work0) trace[4] = gtime_ns();
+        for (int u = 0; u < nunits; ++u) {
+          const int mb = u / nuc, cc = u - mb * nuc;
+          const int col0 = t.n0 + cc * 64;
+          uint8_t* const o0 = buf ? res_buf : out_buf;
+          named_bar_sync(1, 128);  // this pair is free (elected waited for the stores issued two units ago)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN + cc * 64 + half * 32, r);
+            tmem_ld_wait();
+            if (u == nunits - 1 && half == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+            uint8_t* const ob = o0 + half * kEpiBufBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(__uint_as_float(r[4 * j]) * P.alpha, __uint_as_float(r[4 * j + 1]) * P.alpha,
+                                     __uint_as_float(r[4 * j + 2]) * P.alpha, __uint_as_float(r[4 * j + 3]) * P.alpha);
+              if (add_bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbias + cc * 64 + half * 32 + 4 * j);
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              *reinterpret_cast<float4*>(ob + swz(row, j)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (elected) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c0 = col0 + half * 32;
+              if (c0 >= P.n_out) break;
+              const uint8_t* ob = o0 + half * kEpiBufBytes;
+              if (P.partials)  // deterministic split-K: every k-slice owns a slab; a fixed-order pass sums them
+                tma_store_4d(&tmD, ob, c0, t.w0, t.h0 + mb * P.TH, t.img + work / P.total_tiles);
+              else if (P.ksplit > 1 || P.accum)
+                tma_reduce_add_4d(&tmD, ob, c0, t.w0, t.h0 + mb * P.TH, t.img);
+              else
+                tma_store_4d(&tmD, ob, c0, t.w0, t.h0 + mb * P.TH, t.img);
+            }
+            tma_store_commit();
+            tma_store_wait_read<1>();  // the other pair is free again
+          }
+          buf ^= 1;
+        }
+      } else if (P.epi_mode == EPI_TMA_F32) {
         // ---- fp32 NHWC output: 32-column units through swizzled smem + TMA store
         const int cols_left = P.n_out - t.n0;
         int nuc = (cols_left >= BN) ? BN / 32 : (cols_left + 31) / 32;
@@ -485,6 +575,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         mbar_wait(&tfull_bar[as], ap);
         tc_fence_after();
+        if (trace && elected && work == work0) trace[4] = gtime_ns();
         for (int u = 0; u < nunits; ++u) {
           const int mb = u / nuc, cc = u - mb * nuc;
           const int col0 = t.n0 + cc * 32;
@@ -596,8 +687,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cols_left = P.n_out - t.n0;
         const int nuc = (cols_left >= BN) ? BN / 64 : (cols_left + 63) / 64;
         const int nunits = MBLK * nuc;
+        // the tile's column bias goes to shared memory while the contraction is still running (its L2 round trips
+        // used to sit between every tcgen05.ld and the stores); visible after the first named barrier below
+        // (single buffer: whoever gets here has passed the previous tile's last named barrier, which every thread
+        // reaches only after its last read of the previous bias)
+        float* const sb = sbias;
+        if (P.bias_mode == T2H_BIAS_COL) {
+          for (int i = threadIdx.x - 128; i < BN; i += 128)
+            sb[i] = (t.n0 + i < P.n_out) ? __ldg(P.bias + t.img * P.bias_sn + t.n0 + i) : 0.f;
+        }
         mbar_wait(&tfull_bar[as], ap);
         tc_fence_after();
+        if (trace && elected && work == work0) trace[4] = gtime_ns();
         for (int u = 0; u < nunits; ++u) {
           const int mb = u / nuc, cc = u - mb * nuc;
           const int col0 = t.n0 + cc * 64;
@@ -606,9 +707,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool row_ok = (h < P.H) && (w < P.W);
           const float row_bias =
               (P.bias_mode == T2H_BIAS_ROW && row_ok) ? __ldg(P.bias + h * P.W + w) : 0.f;
-          uint8_t* ohi = out_buf;
-          uint8_t* olo = out_buf + kEpiBufBytes;
-          named_bar_sync(1, 128);  // both staging tiles free (elected waited on the previous stores)
+          // two pairs of staging tiles (the residual tiles are unused in this mode): unit u + 1 is converted while
+          // unit u's TMA stores still read theirs
+          uint8_t* ohi = buf ? res_buf : out_buf;
+          uint8_t* olo = ohi + kEpiBufBytes;
+          named_bar_sync(1, 128);  // this pair is free (elected waited for the stores issued two units ago)
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t r[32];
@@ -627,11 +730,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (P.bias_mode == T2H_BIAS_COL) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                if (col0 + half * 32 + i < P.n_out) {  // n_out % 8 == 0 in this mode
-                  const float4 b4 =
-                      __ldg(reinterpret_cast<const float4*>(P.bias + t.img * P.bias_sn + col0 + half * 32 + i));
-                  v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                }
+                const float4 b4 = *reinterpret_cast<const float4*>(sb + cc * 64 + half * 32 + i);  // broadcast read
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
             }
             if (P.act == T2H_ACT_GELU) {
@@ -662,14 +762,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (P.d_terms == 2)
               tma_store_4d(&tmD, olo, col0, t.w0, t.h0 + mb * P.TH, t.img + P.d_term_imgs);
             tma_store_commit();
-            tma_store_wait_read<0>();
+            tma_store_wait_read<1>();  // the other pair of staging tiles is free again
           }
+          buf ^= 1;
         }
       } else {
         // ---- direct path: strided / tiny outputs (NCHW conv_out, n_out < 32, unaligned)
         constexpr int CH = C::kChunk;
         mbar_wait(&tfull_bar[as], ap);
         tc_fence_after();
+        if (trace && elected && work == work0) trace[4] = gtime_ns();
 #pragma unroll 1
         for (int mb = 0; mb < MBLK; ++mb) {
           const int h = t.h0 + mb * P.TH + th;
@@ -744,6 +846,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (elected) tma_store_wait_read<0>();
+    if (trace && elected) trace[5] = gtime_ns();
   }
 
   tc_fence_before();
@@ -885,8 +988,15 @@ static int launch_swap(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 using namespace t2h;
 
 extern "C" int t2h_debug_read(long long* out, int n) {
-  if (n > 148 * 4) n = 148 * 4;
-  T2H_CUDA(cudaMemcpyFromSymbol(out, g_t2h_dbg, sizeof(long long) * n));
+  // out[0] = records written so far (the ring keeps the last kTraceRecords), then up to (n - 1) / 8 records
+  T2H_CHECK_ARG(out && n >= 1, "debug_read: bad args");
+  unsigned int cnt = 0;
+  T2H_CUDA(cudaDeviceSynchronize());
+  T2H_CUDA(cudaMemcpyFromSymbol(&cnt, g_t2h_dbg_n, sizeof(cnt)));
+  out[0] = cnt;
+  int words = n - 1;
+  if (words > kTraceRecords * 8) words = kTraceRecords * 8;
+  if (words > 0) T2H_CUDA(cudaMemcpyFromSymbol(out + 1, g_t2h_dbg, sizeof(long long) * words));
   return T2H_OK;
 }
 
