@@ -7,7 +7,8 @@
 //   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=BN, K=16) on shifted views
 //                           of the slab; accumulators live in tensor memory, double-buffered
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      tcgen05.ld -> alpha/bias/GELU/residual/GroupNorm
+//   warps 4-11 epilogue     (8-11 only in the plane / plain-fp32 modes, taking the upper 32 columns of each
+//                           64-column unit) tcgen05.ld -> alpha/bias/GELU/residual/GroupNorm
 //                           partial sums -> swizzled smem staging -> TMA store
 //                           (residual tiles arrive by TMA load into smem)
 //
@@ -88,7 +89,7 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 
 constexpr int kBK = 64;                      // fp16 elements per 128-byte swizzled row
 constexpr int kABlockBytes = 128 * 128;      // one 128-row A block of a stage
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // warps 0-3 roles below, warps 4-7 and 8-11 two epilogue groups
 constexpr int kEpiBufBytes = 128 * 128;      // one staging tile: 128 rows x 128 bytes
 constexpr int kEpiBytes = 4 * kEpiBufBytes;  // 2 output + 2 residual staging tiles
 
@@ -212,6 +213,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Two epilogue warp groups (warps 4-7: columns 0..31 of every 64-column unit, warps 8-11: columns 32..63) in the
+  // modes whose epilogue is pure per-element work; the residual / GroupNorm-statistics / strided paths keep one.
+  bool two_groups = false;
+  if constexpr (BN >= 64) {
+    two_groups = P.epi_mode == EPI_TMA_PLANES ||
+                 (P.epi_mode == EPI_TMA_F32 && !P.residual && !P.gn_stats && P.act == T2H_ACT_NONE && !P.wg_pair &&
+                  P.bias_mode != T2H_BIAS_ROW && !(P.debug & 1));
+  }
+  const int n_epi = two_groups ? 256 : 128;  // threads at the epilogue's named barriers
   __shared__ unsigned long long* trace_s;  // this launch's trace record (CTA 0, T2H_DEBUG bit 16), else null
 
   if (warp == 0 && lane == 0) {
@@ -238,7 +248,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], two_groups ? 8 : 4);
       mbar_init(&res_bar[s], 1);
     }
     fence_mbar_init();
@@ -471,9 +481,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (warp < 8 || two_groups)) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int grp = (warp - 4) >> 2;  // 0: warps 4-7, 1: warps 8-11
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int th = row / P.TW, tw = row - th * P.TW;
     const bool elected = (threadIdx.x == 128);
@@ -488,11 +499,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ch1 = min(P.kchunks, ch0 + P.kper);
       const TileCoord t = decode_tile(P, tile, MBLK, BN);
 
-      bool plain_f32 = false;
-      if constexpr (BN >= 64) {
-        plain_f32 = P.epi_mode == EPI_TMA_F32 && !P.residual && !P.gn_stats && P.act == T2H_ACT_NONE && !P.wg_pair &&
-                    P.bias_mode != T2H_BIAS_ROW && !(P.debug & 1);
-      }
+      const bool plain_f32 = two_groups && P.epi_mode == EPI_TMA_F32;
       if (plain_f32) {
         // ---- fp32 output with nothing but alpha / column bias in the epilogue (split-K slices, weight gradients,
         // plain projections): 64-column units = two 32-column staging tiles, two pairs of them, so that a unit is
@@ -503,7 +510,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nunits = MBLK * nuc;
         const bool add_bias = P.bias_mode == T2H_BIAS_COL && ch0 == 0;  // split-K: the first k-slice carries the bias
         if (add_bias) {
-          for (int i = threadIdx.x - 128; i < BN; i += 128)
+          for (int i = threadIdx.x - 128; i < BN; i += 256)
             sbias[i] = (t.n0 + i < P.n_out) ? __ldg(P.bias + t.img * P.bias_sn + t.n0 + i) : 0.f;
         }
         mbar_wait(&tfull_bar[as], ap);
@@ -513,13 +520,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int mb = u / nuc, cc = u - mb * nuc;
           const int col0 = t.n0 + cc * 64;
           uint8_t* const o0 = buf ? res_buf : out_buf;
-          named_bar_sync(1, 128);  // this pair is free (elected waited for the stores issued two units ago)
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          named_bar_sync(1, n_epi);  // this pair is free (elected waited for the stores issued two units ago)
+          {
+            const int half = grp;
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN + cc * 64 + half * 32, r);
             tmem_ld_wait();
-            if (u == nunits - 1 && half == 1) {
+            if (u == nunits - 1) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -537,7 +544,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(2, n_epi);
           if (elected) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -693,7 +700,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // reaches only after its last read of the previous bias)
         float* const sb = sbias;
         if (P.bias_mode == T2H_BIAS_COL) {
-          for (int i = threadIdx.x - 128; i < BN; i += 128)
+          for (int i = threadIdx.x - 128; i < BN; i += n_epi)
             sb[i] = (t.n0 + i < P.n_out) ? __ldg(P.bias + t.img * P.bias_sn + t.n0 + i) : 0.f;
         }
         mbar_wait(&tfull_bar[as], ap);
@@ -711,15 +718,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // unit u's TMA stores still read theirs
           uint8_t* ohi = buf ? res_buf : out_buf;
           uint8_t* olo = ohi + kEpiBufBytes;
-          named_bar_sync(1, 128);  // this pair is free (elected waited for the stores issued two units ago)
+          named_bar_sync(1, n_epi);  // this pair is free (elected waited for the stores issued two units ago)
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int half = two_groups ? grp : 0; half < (two_groups ? grp + 1 : 2); ++half) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * C::kAccCols + mb * BN +
                                    cc * 64 + half * 32;
             tmem_ld_32x32(taddr, r);
             tmem_ld_wait();
-            if (u == nunits - 1 && half == 1) {
+            if (u == nunits - 1 && (two_groups || half == 1)) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -756,7 +763,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
+          named_bar_sync(2, n_epi);
           if (elected) {
             tma_store_4d(&tmD, ohi, col0, t.w0, t.h0 + mb * P.TH, t.img);
             if (P.d_terms == 2)
