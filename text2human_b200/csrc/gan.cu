@@ -154,7 +154,7 @@ __global__ void norm_bwd_apply_kernel(const float* __restrict__ x, const double*
       const float du = ds[e] * act_grad(xh * ga[c] + be[c], act);
       r[e] = rstd[c] * (du * ga[c] - m1[c] - xh * m2[c]) + as[e];
     }
-    *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);
+    if (dx) *reinterpret_cast<float4*>(dx + o) = make_float4(r[0], r[1], r[2], r[3]);  // null: only the planes are consumed
     if (dx_colsum) {
       if (fixed_cols) {
 #pragma unroll
@@ -517,7 +517,7 @@ extern "C" {
 int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
                  const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
                  int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, t2h_stream_t stream) {
-  T2H_CHECK_ARG(x && stats && gamma && beta && dy && dx && ws && n > 0 && hw > 0, "norm_bwd: bad args");
+  T2H_CHECK_ARG(x && stats && gamma && beta && dy && (dx || dx_planes) && ws && n > 0 && hw > 0, "norm_bwd: bad args");
   T2H_CHECK_ARG(c % groups == 0 && c % 4 == 0 && c <= 2048, "norm_bwd: C=%d groups=%d unsupported", c, groups);
   T2H_CHECK_ARG(act >= 0 && act <= 2 && (terms == 1 || terms == 2 || !dx_planes), "norm_bwd: act=%d terms=%d", act,
                 terms);

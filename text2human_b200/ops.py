@@ -1160,20 +1160,18 @@ def norm_stats(x, groups, n=None):
 
 
 def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=None, add=None, want_planes=False,
-             n=None, terms=None, colsum_out=None):
+             n=None, terms=None, colsum_out=None, want_dx=True):
     """backward of act(norm(x)*gamma+beta): -> dx fp32 (+ add) [, planes of dx]; dgamma/dbeta accumulated;
-    ``colsum_out`` [C] += column sums of dx (the bias gradient of the conv that produced x)"""
+    ``colsum_out`` [C] += column sums of dx (the bias gradient of the conv that produced x); ``want_dx=False``
+    (with ``want_planes``) skips the fp32 copy when only the conv gradients consume dx (4 of 14 B per element)"""
     _need_cuda(x, dy)
     N, H, W, Cc = x.shape
     terms = terms or get_terms()
     nn_, hw = (N, H * W) if n is None else (n, N * H * W // n)
-    dx = torch.empty_like(x)
+    assert want_dx or want_planes
+    dx = torch.empty_like(x) if want_dx else None
     planes = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device) if want_planes else None
-    import os as _os
-    if _os.environ.get("T2H_WS_ZEROS"):
-        ws = torch.zeros((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
-    else:
-        ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
+    ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
     assert dy.is_contiguous() and x.is_contiguous() and (add is None or add.is_contiguous())
     _count(3)
     _lib.check(_lib.load().t2h_norm_bwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add), _ptr(dx),

@@ -364,7 +364,7 @@ class ResL(Layer):
         d_a2 = G.dgrad("k3", dop, c2.wt, n=N, in_hw=(H, W))
         d_h1, d_h1p = ops.norm_bwd(h1, st2, b.norm2.weight.detach(), b.norm2.bias.detach(), d_a2, act="swish",
                                    groups=32, eps=b.norm2.eps, dgamma=self.gof(b.norm2.weight),
-                                   dbeta=self.gof(b.norm2.bias), want_planes=True,
+                                   dbeta=self.gof(b.norm2.bias), want_planes=True, want_dx=False,
                                    colsum_out=c1.gb[:h1.shape[-1]] if c1.gb is not None else None)   # conv1's bias gradient
         self.tr.done(b.norm2)
         del d_a2, a2, h1
@@ -601,11 +601,6 @@ class DiscNet(Layer):
             i += 3
         self.last = mods[-1]
 
-    @staticmethod
-    def _dbg(t):
-        # checksum only: holding the tensor itself would change which memory blocks the following ops reuse
-        return torch.stack((t.double().sum(), t.double().abs().sum(), (t.double() ** 2).sum()))
-
     def order(self):
         out = [self.last]
         for conv, bn, _ in reversed(self.mid):
@@ -651,30 +646,22 @@ class DiscNet(Layer):
             G.wgrad("k4s1", dlp, h, cl.gw, n=N)
             self.tr.done(self.last)
         g = G.dgrad("k4s1", dlp, cl.wt, n=N, in_hw=(hh, ww))
-        dbg = getattr(self, "debug_trace", None)
-        if dbg is not None:
-            dbg.append(("d_h_last", self._dbg(g)))
         for conv, bn, kind in reversed(self.mid):
             a, pre, st, hh, ww = rec.pop()
             cp = self.cp(conv)
             Cc = pre.shape[-1]
             dpre, dprep = ops.norm_bwd(pre, st, bn.weight.detach(), bn.bias.detach(), g, act="lrelu", groups=Cc,
                                        eps=bn.eps, dgamma=self.gof(bn.weight) if want_params else None,
-                                       dbeta=self.gof(bn.bias) if want_params else None, want_planes=True, n=1)
+                                       dbeta=self.gof(bn.bias) if want_params else None, want_planes=True, n=1,
+                                       want_dx=False)
             if want_params:
                 self.tr.done(bn)
                 G.wgrad(kind, dprep, a, cp.gw, n=N)
                 self.tr.done(conv)
-            if dbg is not None:
-                dbg.append(("dpre", self._dbg(dpre)))
             g = G.dgrad(kind, dprep, cp.wt, n=N, in_hw=(hh, ww))
-            if dbg is not None:
-                dbg.append(("d_h", self._dbg(g)))
         a0, y0, H, W = rec.pop()
         c0 = self.cp(self.first)
         dpre, dprep = ops.lrelu_bwd(y0, g)
-        if dbg is not None:
-            dbg.append(("dpre0", self._dbg(dpre)))
         if want_params:
             self.bias_grad(c0, dpre)
             G.wgrad("k4s2", dprep, a0, c0.gw, n=N)
@@ -824,14 +811,6 @@ class VQGANTrainer:
         self.dec_out.wgrad_only(g_nll, rg)
         self.dec_out.wgrad_only(g_g, gg)
         ops.adaptive_weight(rg, gg, dw, 1.0 / S, self.disc_weight_max, 1.0 if step >= self.disc_start_step else 0.0)
-        import os
-        if os.environ.get("T2H_TRAIN_DEBUG"):
-            print("[train debug] |rg| %.6e |gg| %.6e S %g dw %.6f |g_nll| %.6e |g_g| %.6e" % (
-                float(rg.norm()) / S, float(gg.norm()) / S, S, float(dw[0]), float(g_nll.norm()) / S,
-                float(g_g.norm()) / S))
-            print("[train debug] |xrec| %.8e |xr| %.8e |logits| %.8e |d_lf| %.8e |d_xr| %.8e r %s t %s" % (
-                float(xrec.norm()), float(xr.norm()), float(logits_fake.norm()), float(d_lf.norm()),
-                float(d_xr.norm()) / S, r.tolist(), t.tolist()))
         dxrec = ops.axpy_dev(g_nll, g_g, dw)                 # loss = nll + d_weight * g_loss + codebook_loss
         self._arm(self.gen, last)
         self.gen_backward(dxrec, S)
