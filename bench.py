@@ -178,6 +178,25 @@ def side_workloads(dev, precision):
         l0 = ops.COUNTERS["launches"]
         sm.sample_fn(segm, tm, sample_steps=2, generator=gen, use_graph=False)
         out["config4_sampler"]["launches_per_step"] = (ops.COUNTERS["launches"] - l0) // 2
+        # informational: the same sampler with single-product fp16 operands (not the parity mode; logits within 2e-3
+        # of the reference instead of 6e-6) -- separates the tensor-issue share of a step from its serial latency
+        if precision != "fp16":
+            old_terms = ops.get_terms()
+            try:
+                ops.set_precision("fp16")
+                sm.sample_fn(segm, tm, sample_steps=4, generator=gen)
+                torch.cuda.synchronize()
+                e0.record()
+                sm.sample_fn(segm, tm, sample_steps=64, generator=gen)
+                e1.record()
+                torch.cuda.synchronize()
+                ms16 = e0.elapsed_time(e1) / 64
+                out["config4_sampler"]["single_product_fp16"] = dict(ms_per_diffusion_step=ms16, measured_steps=64,
+                                                                     algorithmic_tflops=4 * 99.86 / ms16)
+            except Exception as exc:  # noqa: BLE001
+                out["config4_sampler"]["single_product_fp16"] = dict(error=repr(exc))
+            finally:
+                ops._PRECISION["terms"] = old_terms
         # the refine half of sample_and_refine: sampled top tokens -> top codebook gather -> UNet/FCN
         # index prediction -> bottom gather -> DecoderRes -> Decoder, batched (the reference decodes one by one)
         del sm
