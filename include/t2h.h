@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define T2H_VERSION 200
+#define T2H_VERSION 201
 
 #define T2H_OK 0
 #define T2H_EINVAL (-1)   /* bad argument / unsupported shape            */
@@ -164,6 +164,19 @@ typedef struct t2h_tapgemm_params {
   float a_gn_eps;
   int32_t a_gn_swish;
   int32_t a_gn_groups;
+  /* Norm-backward sums in the epilogue (swapped-operand kernel: spatial convs with n_out % 128 == 0 and a plain fp32
+   * NHWC destination): for a data-gradient conv whose output D is the gradient w.r.t. act(norm(x)*gamma+beta), with
+   * nb_sums != NULL `residual` holds x (fp32, D's geometry; it is NOT added) and the epilogue accumulates
+   * nb_sums[(img*n_out + c)*2 + {0,1}] += sum over the pixels of {du, du*xhat}, du = D * act'(xhat*gamma+beta),
+   * xhat from nb_stats (as t2h_gn_stats / the conv epilogue produced them) -- pass 1 of t2h_norm_bwd rides along.
+   * nb_act: 0 none, 1 swish, 2 LeakyReLU(0.2); nb_groups: GroupNorm groups (n_out % nb_groups == 0). */
+  double* nb_sums;
+  const double* nb_stats;
+  const float* nb_gamma;
+  const float* nb_beta;
+  float nb_eps;
+  int32_t nb_act;
+  int32_t nb_groups;
 } t2h_tapgemm_params;
 
 int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream);
@@ -411,10 +424,13 @@ int t2h_conv_wgrad(const t2h_conv_wgrad_params* p, t2h_stream_t stream);
  * produced them.  dx = add (optional) + dL/dx as fp32 and / or fp16 planes (either may be NULL, not both: a
  * gradient only the following conv gradients consume needs no fp32 copy); dgamma/dbeta accumulated (may be NULL).
  * ws: 2*n*c doubles of scratch.  act: 0 none, 1 swish, 2 LeakyReLU(0.2).  dx_colsum (optional, [c], accumulated):
- * column sums of the dx written = the bias gradient of the conv whose output x is. */
+ * column sums of the dx written = the bias gradient of the conv whose output x is.  sums_ready != 0: ws already
+ * holds pass 1's per-(image, channel) sums {sum du, sum du*xhat} -- the data-gradient conv that produced dy
+ * accumulated them in its epilogue (t2h_tapgemm_params.nb_sums) -- and only the apply pass runs. */
 int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
                  const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
-                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, t2h_stream_t stream);
+                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, int sums_ready,
+                 t2h_stream_t stream);
 /* BatchNorm2d running statistics: r = (1-momentum) r + momentum * batch (unbiased variance); stats [c][2] */
 int t2h_bn_update_running(const double* stats, float* running_mean, float* running_var, int64_t count,
                           float momentum, int c, t2h_stream_t stream);

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.t2h_version() == 200
+    assert lib.t2h_version() == 201
     assert isinstance(lib.t2h_last_error(), bytes)
 
 

@@ -246,3 +246,50 @@ def test_sample_step_draws_the_categorical_law(cuda):
         ops.sample_step(logits, torch.zeros(M, device=cuda), tex, xx, torch.zeros(M, dtype=torch.uint8, device=cuda),
                         t=1, temp=temp, seed=9, step=st, n_heads=18)
     assert torch.equal(xa, xb) and not torch.equal(xa, xc)
+
+
+@pytest.mark.parametrize("N,H,W,C,act", [(2, 64, 32, 128, "swish"), (1, 40, 24, 256, "swish"), (2, 32, 16, 128, "lrelu")])
+def test_norm_backward_sums_fused_into_the_data_gradient_conv(cuda, N, H, W, C, act):
+    """t2h_tapgemm_params.nb_sums: pass 1 of the GroupNorm backward (sum du, sum du*xhat per image and channel)
+    accumulated in the epilogue of the 3x3 data-gradient conv that produces dy, against the stand-alone reduce pass of
+    t2h_norm_bwd and an fp64 restatement; the conv's own output must not change."""
+    from text2human_b200 import conv_grad as G
+    from text2human_b200 import ops
+    ops.set_precision("fp32")
+    g = torch.Generator(device=cuda).manual_seed(N * H + C)
+    Co = 128
+    x = torch.randn(N, H, W, C, device=cuda, generator=g) * 1.5 + 0.3        # the norm's input
+    gamma = torch.randn(C, device=cuda, generator=g)
+    beta = torch.randn(C, device=cuda, generator=g)
+    w = torch.randn(Co, C, 3, 3, device=cuda, generator=g) / (9 * C) ** 0.5     # the conv that consumed act(norm(x))
+    gy = torch.randn(N, H, W, Co, device=cuda, generator=g)                   # gradient w.r.t. the conv output
+    st = ops.norm_stats(x, 32)
+    wn, wt = G.weight_planes(G.oihw_to_master(w), 2)
+    gyp = ops.f32_to_planes(gy, ops.CVT_PLAIN)
+    nb = ops.nb_context(x, st, gamma, beta, act=act, groups=32, eps=1e-6)
+    assert nb is not None
+    da_f = G.dgrad("k3", gyp, wt, n=N, in_hw=(H, W), nb=nb)
+    da_p = G.dgrad("k3", gyp, wt, n=N, in_hw=(H, W))
+    assert torch.equal(da_f, da_p)
+    # fp64 restatement of pass 1
+    xd = x.double()
+    xg = xd.view(N, H * W, 32, C // 32)
+    mean = xg.mean(dim=(1, 3), keepdim=True)
+    var = xg.var(dim=(1, 3), unbiased=False, keepdim=True)
+    xh = ((xg - mean) / torch.sqrt(var + 1e-6)).view(N, H, W, C)
+    u = xh * gamma.double() + beta.double()
+    if act == "swish":
+        s = torch.sigmoid(u)
+        dact = s * (1 + u * (1 - s))
+    else:
+        dact = torch.where(u > 0, torch.ones_like(u), torch.full_like(u, 0.2))
+    du = da_p.double() * dact
+    ref = torch.stack((du.sum(dim=(1, 2)), (du * xh).sum(dim=(1, 2))), dim=-1)   # [N, C, 2]
+    got = nb["sums"].view(N, C, 2)
+    e = ((got - ref).abs().max() / ref.abs().max()).item()
+    print(f"[nb] fused pass-1 sums vs fp64: {e:.2e}")
+    assert e < 2e-5
+    # the full backward with and without the fused sums
+    dx_f, dxp_f = ops.norm_bwd(x, st, gamma, beta, da_f, act=act, groups=32, eps=1e-6, want_planes=True, sums=nb["sums"])
+    dx_p, dxp_p = ops.norm_bwd(x, st, gamma, beta, da_p, act=act, groups=32, eps=1e-6, want_planes=True)
+    assert ((dx_f - dx_p).abs().max() / dx_p.abs().max()).item() < 1e-5

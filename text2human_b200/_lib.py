@@ -44,6 +44,8 @@ class TapGemmParams(C.Structure):
         ("k_partials", C.c_int32), ("d_slab", C.c_int64),
         ("a_f32", C.c_void_p), ("a_gn_stats", C.c_void_p), ("a_gn_gamma", C.c_void_p), ("a_gn_beta", C.c_void_p),
         ("a_gn_eps", C.c_float), ("a_gn_swish", C.c_int32), ("a_gn_groups", C.c_int32),
+        ("nb_sums", C.c_void_p), ("nb_stats", C.c_void_p), ("nb_gamma", C.c_void_p), ("nb_beta", C.c_void_p),
+        ("nb_eps", C.c_float), ("nb_act", C.c_int32), ("nb_groups", C.c_int32),
     ]
 
 
@@ -107,7 +109,7 @@ SIGNATURES = {
     "t2h_embed_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P]),
     "t2h_adam": (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
     "t2h_conv_wgrad": (_I, [C.POINTER(ConvWgradParams), _P]),
-    "t2h_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "t2h_norm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _I, _P]),
     "t2h_bn_update_running": (_I, [_P, _P, _P, _L, _F, _I, _P]),
     "t2h_lrelu_bwd": (_I, [_P, _P, _P, _P, _I, _L, _P]),
     "t2h_sumpool2": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -71,7 +71,7 @@ def forward(kind, a, wn, bias, *, n, in_hw, **kw):
     return ops.tap_conv(a, wn, bias, fwd_taps(kind, n), n=n, out_hw=out_hw(kind, *in_hw), **kw)
 
 
-def dgrad(kind, dyp, wt, *, n, in_hw, cin=None, out=None, d_strides=None):
+def dgrad(kind, dyp, wt, *, n, in_hw, cin=None, out=None, d_strides=None, nb=None):
     """dX fp32 [N,H,W,Cin_p] (or into ``out`` with element strides ``d_strides`` = (sn, sh, sw, sc) of the FULL
     input grid, e.g. an NCHW image gradient) from dY planes [T,N,Ho,Wo,Cout_p] and transposed planes
     wt [T,taps,Cin_p,Cout_p]; ``cin`` limits the computed input channels (image gradients: 3 of 8)."""
@@ -82,8 +82,10 @@ def dgrad(kind, dyp, wt, *, n, in_hw, cin=None, out=None, d_strides=None):
     if STRIDE[kind] == 1:
         taps = tuple((-ty, -tx, 0) for ty, tx, _ in fwd_taps(kind, n))
         if out is None:
-            return ops.tap_conv(dyp, wt, None, taps, n=n, out_hw=(H, W))
+            return ops.tap_conv(dyp, wt, None, taps, n=n, out_hw=(H, W), nb=nb)   # nb: ops.nb_context (norm-backward sums)
+        assert nb is None
         return ops.tap_conv(dyp, wt, None, taps, n=n, out_hw=(H, W), out=out, d_strides=d_strides)
+    assert nb is None, "norm-backward sums ride only on single-launch (stride-1) data gradients"
     if out is None:
         out = torch.empty((n, H, W, ci), dtype=torch.float32, device=dyp.device)
         d_strides = (H * W * ci, W * ci, ci, 1)

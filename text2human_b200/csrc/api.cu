@@ -17,15 +17,15 @@ int fail(int code, const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return 148;
-    cached = n;
+  static int cached[64] = {};  // per device of this process (0 = not queried yet)
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = cached[dev & 63];
+  if (c <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    c = n;
   }
-  return cached;
+  return c;
 }
 
 }  // namespace t2h

@@ -19,16 +19,6 @@ static inline int grid_cap(long long work, int block, int per_sm = 16) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
-// derivative of the activation that follows the norm, as a function of the pre-activation u
-__device__ __forceinline__ float act_grad(float u, int act) {
-  if (act == 1) {  // swish: u*sigmoid(u)
-    const float s = 1.0f / (1.0f + __expf(-u));
-    return s * (1.0f + u * (1.0f - s));
-  }
-  if (act == 2) return u > 0.f ? 1.0f : 0.2f;  // LeakyReLU(0.2)
-  return 1.0f;
-}
-
 // per-channel constants of one image's normalisation, in shared memory: mean, rstd, gamma, beta
 __device__ __forceinline__ void norm_consts(const double* __restrict__ stats, const float* __restrict__ gamma,
                                             const float* __restrict__ beta, int n, int C, int groups, int HW,
@@ -516,26 +506,29 @@ extern "C" {
 
 int t2h_norm_bwd(const float* x, const double* stats, const float* gamma, const float* beta, const float* dy,
                  const float* add, float* dx, void* dx_planes, int terms, float* dgamma, float* dbeta, double* ws,
-                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, t2h_stream_t stream) {
+                 int n, int hw, int c, int groups, float eps, int act, float* dx_colsum, int sums_ready,
+                 t2h_stream_t stream) {
   T2H_CHECK_ARG(x && stats && gamma && beta && dy && (dx || dx_planes) && ws && n > 0 && hw > 0, "norm_bwd: bad args");
   T2H_CHECK_ARG(c % groups == 0 && c % 4 == 0 && c <= 2048, "norm_bwd: C=%d groups=%d unsupported", c, groups);
   T2H_CHECK_ARG(act >= 0 && act <= 2 && (terms == 1 || terms == 2 || !dx_planes), "norm_bwd: act=%d terms=%d", act,
                 terms);
   cudaStream_t st = as_stream(stream);
-  T2H_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)n * c, st));
-  const int c4 = c / 4;
-  int block = 256;
-  if (c4 > block) block = ((c4 + 31) / 32) * 32;
-  T2H_CHECK_ARG(block <= 1024, "norm_bwd: C=%d too large", c);
-  block = (block / c4) * c4;
-  const int lanes = block / c4;
-  int blocks_x = ceil_div(num_sms() * 4, n);
-  int ppb = ceil_div(hw, blocks_x);
-  if (ppb < lanes * 8) ppb = lanes * 8;
-  blocks_x = ceil_div(hw, ppb);
-  norm_bwd_reduce_kernel<<<dim3(blocks_x, n), block, 6 * c * sizeof(float), st>>>(x, stats, gamma, beta, dy, ws, hw,
-                                                                               c, groups, eps, act, ppb);
-  T2H_LAUNCH_OK();
+  if (!sums_ready) {  // pass 1 (skipped when the conv that produced dy accumulated the sums in its epilogue)
+    T2H_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)n * c, st));
+    const int c4 = c / 4;
+    int block = 256;
+    if (c4 > block) block = ((c4 + 31) / 32) * 32;
+    T2H_CHECK_ARG(block <= 1024, "norm_bwd: C=%d too large", c);
+    block = (block / c4) * c4;
+    const int lanes = block / c4;
+    int blocks_x = ceil_div(num_sms() * 4, n);
+    int ppb = ceil_div(hw, blocks_x);
+    if (ppb < lanes * 8) ppb = lanes * 8;
+    blocks_x = ceil_div(hw, ppb);
+    norm_bwd_reduce_kernel<<<dim3(blocks_x, n), block, 6 * c * sizeof(float), st>>>(x, stats, gamma, beta, dy, ws,
+                                                                                 hw, c, groups, eps, act, ppb);
+    T2H_LAUNCH_OK();
+  }
   int bx2 = ceil_div(num_sms() * 8, n);
   int ppb2 = ceil_div(hw, bx2);
   if (ppb2 < 16) ppb2 = 16;

@@ -71,6 +71,13 @@ struct TapGemmDev {
   float ag_eps;
   int ag_swish, ag_groups, ag_hw, ag_H, ag_W;
   int partials;  // split-K without reduction: k-slice s of a tile is stored to image slot t.img + s of D
+  // norm-backward sums in the swapped kernel's epilogue (see t2h_tapgemm_params.nb_sums): `residual` is x
+  double* nb_sums;
+  const double* nb_stats;
+  const float *nb_gamma, *nb_beta;
+  float nb_eps;
+  int nb_act, nb_groups;
+  int n_major;  // tile index = column tile * row tiles + row tile (set with nb_sums; default is row-major)
   int wg_PW, wg_PH, wg_pw, wg_ppi;
   int wg_dy[T2H_MAX_TAPS], wg_dx[T2H_MAX_TAPS], wg_ioff[T2H_MAX_TAPS];
 };
@@ -117,6 +124,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TapGemmDev& P, int tile, 
   TileCoord t;
   int n_tile = tile % P.n_tiles_n;
   int m_tile = tile / P.n_tiles_n;
+  if (P.n_major) {  // column tile is the slow index: a contiguous tile range stays on one (column block, image)
+    const int mt = P.total_tiles / P.n_tiles_n;
+    n_tile = tile / mt;
+    m_tile = tile - n_tile * mt;
+  }
   if (P.pair) {
     // `tile` enumerates (row-tile pair, column tile); this CTA takes row 2*pair + rank.  An odd row count
     // leaves the last pair's second CTA with an out-of-range row tile (zero-filled loads, clipped stores).
@@ -1035,6 +1047,9 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
   P.d_sn = p->d_sn; P.d_sh = p->d_sh; P.d_sw = p->d_sw; P.d_sc = p->d_sc;
   P.bias = p->bias; P.bias_sn = p->bias_mode == T2H_BIAS_COL ? p->bias_sn : 0; P.bias_mode = p->bias_mode; P.act = p->act; P.alpha = p->alpha;
   P.residual = p->residual; P.gn_stats = p->gn_stats; P.gn_cpg = p->gn_cpg;
+  P.nb_sums = p->nb_sums; P.nb_stats = p->nb_stats; P.nb_gamma = p->nb_gamma; P.nb_beta = p->nb_beta;
+  P.nb_eps = p->nb_eps; P.nb_act = p->nb_act; P.nb_groups = p->nb_groups;
+  P.n_major = p->nb_sums ? 1 : 0;
   P.gn_groups = p->gn_cpg > 0 ? p->n_out / p->gn_cpg : 0;
   P.d_term_imgs = 0;
 
@@ -1165,6 +1180,13 @@ extern "C" int t2h_tapgemm(const t2h_tapgemm_params* p, t2h_stream_t stream) {
     tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(p->bias) % 16 == 0) && p->bias_sn % 4 == 0;
   P.epi_mode = !tma_ok ? EPI_DIRECT : (p->d_mode == T2H_OUT_F32 ? EPI_TMA_F32 : EPI_TMA_PLANES);
   if (swap) P.epi_mode = swap_direct ? EPI_DIRECT : EPI_TMA_F32;
+  if (p->nb_sums) {
+    T2H_CHECK_ARG(swap && !swap_direct && p->residual && p->nb_stats && p->nb_gamma && p->nb_beta && !p->gn_stats &&
+                      !p->a_f32 && p->act == T2H_ACT_NONE && p->nb_act >= 0 && p->nb_act <= 2 && p->nb_groups > 0 &&
+                      p->n_out % p->nb_groups == 0 && p->k_split <= 1 && !p->accumulate && !p->k_partials,
+                  "tapgemm: nb_sums needs a swapped-kernel conv (n_out %% 128 == 0, fp32 NHWC output), x in `residual`, "
+                  "statistics / gamma / beta, and no other epilogue work");
+  }
   // ---- split-K: k-slices of one tile go to different CTAs and are reduce-added into a zeroed output
   P.ksplit = 1;
   P.kper = P.kchunks;

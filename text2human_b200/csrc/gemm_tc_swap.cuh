@@ -91,6 +91,13 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // everything above touched only shared / tensor memory and kernel parameters; from here on the previous
   // kernel's results are read (and buffers it may still be reading are overwritten)
   pdl_wait();
+  // tile schedule: round-robin over the CTAs, or -- when the epilogue accumulates per-image sums (nb_sums) -- one
+  // contiguous range per CTA, so that a CTA stays inside one image and flushes its sums once or twice per launch
+  // instead of once per tile (round-robin put ~1000 double atomics per launch on every (image, channel) address)
+  const bool contig = P.nb_sums != nullptr;
+  const int tile_first = contig ? (int)((long long)blockIdx.x * P.total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int tile_end = contig ? (int)((long long)(blockIdx.x + 1) * P.total_tiles / gridDim.x) : P.total_tiles;
+  const int tile_step = contig ? 1 : (int)gridDim.x;
 
   const int a_planes = (P.nterms == 3) ? 2 : 1;
   const int slab_bytes = P.slab_rows * P.TW * 128;
@@ -107,7 +114,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const double cnt = (double)P.ag_hw * cpg;
     int cur_img = -1;
     int sa = 0, pa = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
       if (t.img != cur_img) {
         named_bar_sync(3, 128);  // nobody still reads the previous image's table
@@ -181,7 +188,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ---------------------------------------------- activation slab producer
     if (lane == 0 && !(P.debug & 8)) {
       int sa = 0, pa = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const TileCoord t = decode_tile(P, tile, MBLK, 128);
         for (int g = 0; g < P.ngroups; ++g)
           for (int ch = 0; ch < P.kchunks; ++ch)
@@ -205,7 +212,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ---------------------------------------------- weight tile producer (128 couts x 64 k)
     if (lane == 0 && !(P.debug & 8)) {
       int sb = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const TileCoord t = decode_tile(P, tile, MBLK, 128);
         for (int g = 0; g < P.ngroups; ++g)
           for (int ch = 0; ch < P.kchunks; ++ch)
@@ -240,12 +247,8 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool dbg_nobar = (P.debug & 8) != 0, dbg_nomma = (P.debug & 2) != 0;
       const int ngroups = P.ngroups, kchunks = P.kchunks;
       int sa = 0, pa = 0, sb = 0, pb = 0, as = 0, ap = 0;
-      long long n_mma = 0, t_wait = 0, t_exec = 0;
-      const long long t_begin = clock64();
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const long long tw0 = clock64();
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         mbar_wait(&tempty_bar[as], ap ^ 1);
-        t_wait += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_base = tmem_base + as * C::kAccCols;
         uint32_t acc = 0;
@@ -292,26 +295,16 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (!dbg_nobar) { if (elect_one()) umma_commit(&b_empty[sb]); __syncwarp(); }
                 if (++sb == NB) { sb = 0; pb ^= 1; }
               }
-              n_mma += ksteps * (a_planes == 2 ? 3 : 1);
             }
             if (!dbg_nobar) { if (elect_one()) umma_commit(a_planes == 1 ? &a_empty[sa_hi] : &a_empty[sa_lo]); __syncwarp(); }
           }
         }
         { if (elect_one()) umma_commit(&tfull_bar[as]); __syncwarp(); }
-        if (P.debug & 128) {  // experiment: serialise — wait for this tile's MMAs before issuing more
-          mbar_wait(&tfull_bar[as], ap);
-          t_exec += clock64() - tw0;
-        }
+        if (P.debug & 128) mbar_wait(&tfull_bar[as], ap);  // experiment: serialise tiles (wait for this tile's MMAs)
         if (++as == 2) {
           as = 0;
           ap ^= 1;
         }
-      }
-      if ((P.debug & 16) && lane == 0) {
-        g_t2h_dbg[blockIdx.x * 4 + 0] = clock64() - t_begin;
-        g_t2h_dbg[blockIdx.x * 4 + 1] = n_mma;
-        g_t2h_dbg[blockIdx.x * 4 + 2] = t_wait;
-        g_t2h_dbg[blockIdx.x * 4 + 3] = t_exec;
       }
     }
   } else if (warp >= 4 && warp < 4 + EW) {
@@ -332,8 +325,22 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t res_par = 0;
     const int cpg = P.gn_cpg;
     const int red = cpg < 32 ? cpg : 32;  // lanes sharing a GroupNorm group inside this warp
+    const bool nb = P.nb_sums != nullptr;  // norm-backward sums: the "residual" tile is x and is not added
+    float nb_mean = 0.f, nb_rstd = 0.f, nb_ga = 0.f, nb_be = 0.f, nb_s1 = 0.f, nb_s2 = 0.f;
+    int nb_img = -1, nb_c0 = -1;
+    bool nb_fresh = true;
+    auto nb_flush = [&]() {
+      if (nb_img >= 0 && nb_c0 + lane < P.n_out) {
+        double* dst = P.nb_sums + ((long long)nb_img * P.n_out + nb_c0 + lane) * 2;
+        atomicAdd(dst, (double)nb_s1);
+        atomicAdd(dst + 1, (double)nb_s2);
+      }
+      nb_s1 = 0.f;
+      nb_s2 = 0.f;
+      nb_fresh = true;
+    };
 
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
       const int c0 = t.n0 + q * 32;  // this warp's first output channel
       const float bias_c =
@@ -347,6 +354,27 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // interior tiles need no per-pixel validity test for the GroupNorm sums
       const bool interior = (t.h0 + MBLK * P.TH <= P.H) && (t.w0 + P.TW <= P.W);
       float gs = 0.f, gss = 0.f;
+      // norm-backward: this lane's channel constants of image t.img (mean, rstd from the forward statistics); the
+      // sums run on across consecutive tiles of the same (image, channel block) and are flushed when that changes
+      if (nb && (t.img != nb_img || c0 != nb_c0)) {
+        nb_flush();
+        nb_img = t.img;
+        nb_c0 = c0;
+      }
+      if (nb && c0 + lane < P.n_out && nb_fresh) {
+        nb_fresh = false;
+        const int c = c0 + lane;
+        const int ncpg = P.n_out / P.nb_groups;
+        const double cnt = (double)P.H * P.W * ncpg;
+        const double* st = P.nb_stats + ((long long)t.img * P.nb_groups + c / ncpg) * 2;
+        const double m = st[0] / cnt;
+        double var = st[1] / cnt - m * m;
+        if (var < 0) var = 0;
+        nb_mean = (float)m;
+        nb_rstd = (float)(1.0 / sqrt(var + (double)P.nb_eps));
+        nb_ga = __ldg(P.nb_gamma + c);
+        nb_be = __ldg(P.nb_beta + c);
+      }
       mbar_wait(&tfull_bar[as], ap);
       tc_fence_after();
 #pragma unroll 1
@@ -385,9 +413,23 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (has_res) {
           mbar_wait(&res_bar[e], res_par);
           res_par ^= 1;
+          if (nb) {
+            // v = dL/d act(norm(x)); accumulate pass 1 of the norm backward: sum du, sum du*xhat over the pixels
+            const int hrow0 = t.h0 + k * rows_per_chunk;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
-            v[i] += *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+            for (int i = 0; i < 32; ++i) {
+              const float x = *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+              const bool ok = interior || ((hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W));
+              const float xh = (x - nb_mean) * nb_rstd;
+              const float du = ok ? v[i] * act_grad_fast(fmaf(xh, nb_ga, nb_be), P.nb_act) : 0.f;
+              nb_s1 += du;
+              nb_s2 = fmaf(du, xh, nb_s2);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
+              v[i] += *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+          }
           __syncwarp();
           if (lane == 0 && k + KSTEP < NCH) issue_res(k + KSTEP);  // overlaps the rest of this chunk
         }
@@ -452,6 +494,7 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ap ^= 1;
       }
     }
+    if (nb) nb_flush();
     if (lane == 0) tma_store_wait_read<0>();
   }
 

@@ -106,7 +106,7 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
              b, b_term_g, b_groups, b_batched, n_out, b_sn, b_sg, taps, d, d_mode, d_strides,
              d_plane=0, bias=None, bias_mode=BIAS_NONE, act=ACT_NONE, alpha=1.0, residual=None,
              tile_rows=0, b_groups2=1, b_sg2=0, b_batched_h=0, gn_stats=None, gn_cpg=0, k_split=0, bias_sn=0, a_mn=0, b_mn=0,
-             tap_w=None, accumulate=False, k_partials=0, d_slab=0, a_f32=None, gn=None):
+             tap_w=None, accumulate=False, k_partials=0, d_slab=0, a_f32=None, gn=None, nb=None):
     lib = _lib.load()
     Tb = b.shape[0]
     p = TapGemmParams()
@@ -147,6 +147,13 @@ def _tapgemm(*, a, a_term_imgs, a_imgs, a_bcast, n_img, H, W, a_H, a_W, Cc, a_sw
     p.a_mn, p.b_mn = a_mn, b_mn
     p.accumulate = 1 if accumulate else 0
     p.k_partials, p.d_slab = k_partials, d_slab
+    if nb is not None:
+        # norm-backward pass 1 in the epilogue: `residual` carries x (not added), see nb_context
+        assert residual is None
+        p.residual = nb["x"].data_ptr()
+        p.nb_sums = nb["sums"].data_ptr(); p.nb_stats = nb["stats"].data_ptr()
+        p.nb_gamma = nb["gamma"].data_ptr(); p.nb_beta = nb["beta"].data_ptr()
+        p.nb_eps = nb["eps"]; p.nb_act = ACT_CODE[nb["act"]]; p.nb_groups = nb["groups"]
     if tap_w is not None:
         p.use_tap_w = 1
         for i, wi in enumerate(tap_w):
@@ -1054,7 +1061,7 @@ def pack_u8(x, scale=1.0, shift=0.0):
 # losses (csrc/gemm_tc.cu t2h_conv_wgrad, csrc/gan.cu)
 # ----------------------------------------------------------------------------
 def tap_conv(a, w, bias, taps, *, n, out_hw, out=None, d_strides=None, planes_out=False, nchw_out=False, act=ACT_NONE,
-             residual=None, want_stats=False, alpha=1.0, tap_w=None):
+             residual=None, want_stats=False, alpha=1.0, tap_w=None, nb=None):
     """out[img, h, w, :] = act(alpha * sum_i W[tap_w[i]] . a[img + off_i, h + dy_i, w + dx_i, :] + bias) over an
     (out_hw) output domain that may differ from a's spatial extent (reads outside a are zero).
     a: planes whose last three dims are (h, w, C) and whose dims between the plane dim and those flatten to the
@@ -1085,10 +1092,30 @@ def tap_conv(a, w, bias, taps, *, n, out_hw, out=None, d_strides=None, planes_ou
              b_sg=w.stride(1),
              taps=taps, d=out, d_mode=OUT_PLANES if planes_out else OUT_F32, d_strides=d_strides,
              d_plane=n * H * W * Cout, bias=bias, bias_mode=BIAS_COL, act=act, residual=residual, alpha=alpha,
-             gn_stats=stats, gn_cpg=cpg, tap_w=tap_w)
+             gn_stats=stats, gn_cpg=cpg, tap_w=tap_w, nb=nb)
     if want_stats:
         return out, stats
     return out
+
+
+FUSE_NB = {"on": _os_env.environ.get("T2H_FUSE_NB", "1") != "0"}
+
+
+def nb_context(x, stats, gamma, beta, *, act, groups, eps):
+    """Context for fusing pass 1 of ``norm_bwd`` (the per-(image, channel) sums of du and du*xhat) into the epilogue of
+    the data-gradient conv that produces dy = dL/d act(norm(x)*gamma+beta): pass it as ``nb=`` to a stride-1
+    ``conv_grad.dgrad`` whose output has x's shape, then ``norm_bwd(..., sums=ctx["sums"])``.  Returns None when the
+    conv would not run on the swapped-operand kernel (channels % 128, narrow images) or T2H_FUSE_NB=0 -- the caller
+    then simply omits both arguments and norm_bwd runs its own reduce pass."""
+    N, H, W, Cc = x.shape
+    if not FUSE_NB["on"] or Cc % 128 or Cc % groups or H < 2 or os_no_swap() or not x.is_contiguous():
+        return None
+    sums = torch.zeros((N * Cc * 2,), dtype=torch.float64, device=x.device)
+    return dict(x=x, stats=stats, gamma=_f32c(gamma), beta=_f32c(beta), act=act, groups=groups, eps=float(eps), sums=sums)
+
+
+def os_no_swap():
+    return _os_env.environ.get("T2H_NO_SWAP", "0") not in ("", "0")
 
 
 def conv_wgrad(dy, x, taps, dw, *, n, alpha=1.0, k_split=0):
@@ -1160,10 +1187,12 @@ def norm_stats(x, groups, n=None):
 
 
 def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=None, add=None, want_planes=False,
-             n=None, terms=None, colsum_out=None, want_dx=True):
+             n=None, terms=None, colsum_out=None, want_dx=True, sums=None):
     """backward of act(norm(x)*gamma+beta): -> dx fp32 (+ add) [, planes of dx]; dgamma/dbeta accumulated;
     ``colsum_out`` [C] += column sums of dx (the bias gradient of the conv that produced x); ``want_dx=False``
-    (with ``want_planes``) skips the fp32 copy when only the conv gradients consume dx (4 of 14 B per element)"""
+    (with ``want_planes``) skips the fp32 copy when only the conv gradients consume dx (4 of 14 B per element);
+    ``sums``: pass 1's result from ``nb_context`` (the data-gradient conv accumulated it in its epilogue) -- the
+    reduce launch and its 8 B per element are skipped"""
     _need_cuda(x, dy)
     N, H, W, Cc = x.shape
     terms = terms or get_terms()
@@ -1171,12 +1200,16 @@ def norm_bwd(x, stats, gamma, beta, dy, *, act, groups, eps, dgamma=None, dbeta=
     assert want_dx or want_planes
     dx = torch.empty_like(x) if want_dx else None
     planes = torch.empty((terms, N, H, W, Cc), dtype=torch.float16, device=x.device) if want_planes else None
-    ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
+    if sums is not None:
+        assert sums.dtype == torch.float64 and sums.numel() == nn_ * Cc * 2
+        ws = sums
+    else:
+        ws = torch.empty((nn_ * Cc * 2,), dtype=torch.float64, device=x.device)
     assert dy.is_contiguous() and x.is_contiguous() and (add is None or add.is_contiguous())
-    _count(3)
+    _count(3 if sums is None else 2)
     _lib.check(_lib.load().t2h_norm_bwd(_ptr(x), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add), _ptr(dx),
                                         _ptr(planes), terms, _ptr(dgamma), _ptr(dbeta), _ptr(ws), nn_, hw, Cc, groups,
-                                        eps, ACT_CODE[act], _ptr(colsum_out), _stream()))
+                                        eps, ACT_CODE[act], _ptr(colsum_out), 0 if sums is None else 1, _stream()))
     return (dx, planes) if want_planes else dx
 
 

@@ -315,11 +315,14 @@ class NormConvOutL(Layer):
             ops.colsum_(cp.gb[:cp.co], g2.reshape(-1, cp.co))
         G.wgrad("k3", dyp, a, cp.gw, n=N)
         self.tr.done(self.conv)
-        da = G.dgrad("k3", dyp, cp.wt, n=N, in_hw=(H, W))
+        # pass 1 of the norm backward (sum du, sum du*xhat) rides in the data-gradient conv's epilogue where it can
+        nb = ops.nb_context(x, st, self.norm.weight.detach(), self.norm.bias.detach(), act="swish", groups=32,
+                            eps=self.norm.eps)
+        da = G.dgrad("k3", dyp, cp.wt, n=N, in_hw=(H, W), nb=nb)
         cs = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
         dx, dxp = ops.norm_bwd(x, st, self.norm.weight.detach(), self.norm.bias.detach(), da, act="swish", groups=32,
                                eps=self.norm.eps, dgamma=self.gof(self.norm.weight), dbeta=self.gof(self.norm.bias),
-                               want_planes=True, colsum_out=cs)
+                               want_planes=True, colsum_out=cs, sums=nb["sums"] if nb else None)
         self.tr.done(self.norm)
         return Grad(dx, dxp, cs)
 
@@ -361,16 +364,21 @@ class ResL(Layer):
         self.bias_grad(c2, grad)
         G.wgrad("k3", dop, a2, c2.gw, n=N)
         self.tr.done(b.conv2)
-        d_a2 = G.dgrad("k3", dop, c2.wt, n=N, in_hw=(H, W))
+        nb2 = ops.nb_context(h1, st2, b.norm2.weight.detach(), b.norm2.bias.detach(), act="swish", groups=32,
+                             eps=b.norm2.eps)
+        d_a2 = G.dgrad("k3", dop, c2.wt, n=N, in_hw=(H, W), nb=nb2)
         d_h1, d_h1p = ops.norm_bwd(h1, st2, b.norm2.weight.detach(), b.norm2.bias.detach(), d_a2, act="swish",
                                    groups=32, eps=b.norm2.eps, dgamma=self.gof(b.norm2.weight),
                                    dbeta=self.gof(b.norm2.bias), want_planes=True, want_dx=False,
-                                   colsum_out=c1.gb[:h1.shape[-1]] if c1.gb is not None else None)   # conv1's bias gradient
+                                   colsum_out=c1.gb[:h1.shape[-1]] if c1.gb is not None else None,   # conv1's bias gradient
+                                   sums=nb2["sums"] if nb2 else None)
         self.tr.done(b.norm2)
         del d_a2, a2, h1
         G.wgrad("k3", d_h1p, a1, c1.gw, n=N)
         self.tr.done(b.conv1)
-        d_a1 = G.dgrad("k3", d_h1p, c1.wt, n=N, in_hw=(H, W))
+        nb1 = ops.nb_context(x, st1, b.norm1.weight.detach(), b.norm1.bias.detach(), act="swish", groups=32,
+                             eps=b.norm1.eps)
+        d_a1 = G.dgrad("k3", d_h1p, c1.wt, n=N, in_hw=(H, W), nb=nb1)
         del d_h1, d_h1p, a1
         d_sc = grad.g
         if xp is not None:
@@ -382,7 +390,7 @@ class ResL(Layer):
         csum = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
         dx, dxp = ops.norm_bwd(x, st1, b.norm1.weight.detach(), b.norm1.bias.detach(), d_a1, act="swish", groups=32,
                                eps=b.norm1.eps, dgamma=self.gof(b.norm1.weight), dbeta=self.gof(b.norm1.bias),
-                               add=d_sc, want_planes=True, colsum_out=csum)
+                               add=d_sc, want_planes=True, colsum_out=csum, sums=nb1["sums"] if nb1 else None)
         self.tr.done(b.norm1)
         return Grad(dx, dxp, csum)
 
