@@ -326,19 +326,9 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cpg = P.gn_cpg;
     const int red = cpg < 32 ? cpg : 32;  // lanes sharing a GroupNorm group inside this warp
     const bool nb = P.nb_sums != nullptr;  // norm-backward sums: the "residual" tile is x and is not added
+    // (plain locals and an explicit flush at both sites: a by-reference lambda put the running sums in local memory)
     float nb_mean = 0.f, nb_rstd = 0.f, nb_ga = 0.f, nb_be = 0.f, nb_s1 = 0.f, nb_s2 = 0.f;
     int nb_img = -1, nb_c0 = -1;
-    bool nb_fresh = true;
-    auto nb_flush = [&]() {
-      if (nb_img >= 0 && nb_c0 + lane < P.n_out) {
-        double* dst = P.nb_sums + ((long long)nb_img * P.n_out + nb_c0 + lane) * 2;
-        atomicAdd(dst, (double)nb_s1);
-        atomicAdd(dst + 1, (double)nb_s2);
-      }
-      nb_s1 = 0.f;
-      nb_s2 = 0.f;
-      nb_fresh = true;
-    };
 
     for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const TileCoord t = decode_tile(P, tile, MBLK, 128);
@@ -351,19 +341,29 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       if (has_res && lane == 0) issue_res(half);
       constexpr int KSTEP = EW / 4;  // chunks are dealt round-robin to the quadrant's warps
+      if (nb && lane == 0 && tile + tile_step < tile_end) {
+        // the NEXT tile's x boxes go to L2 now, while its MMAs run: the epilogue's own loads then cost an L2 hit
+        // instead of a DRAM round trip under load, four times per tile on the critical path
+        const TileCoord tn = decode_tile(P, tile + tile_step, MBLK, 128);
+        for (int k = half; k < NPIX / 32; k += KSTEP)
+          tma_prefetch_4d(&tmR, tn.n0 + q * 32, tn.w0, tn.h0 + k * rows_per_chunk, tn.img);
+      }
       // interior tiles need no per-pixel validity test for the GroupNorm sums
       const bool interior = (t.h0 + MBLK * P.TH <= P.H) && (t.w0 + P.TW <= P.W);
       float gs = 0.f, gss = 0.f;
       // norm-backward: this lane's channel constants of image t.img (mean, rstd from the forward statistics); the
       // sums run on across consecutive tiles of the same (image, channel block) and are flushed when that changes
       if (nb && (t.img != nb_img || c0 != nb_c0)) {
-        nb_flush();
+        if (nb_img >= 0 && nb_c0 + lane < P.n_out) {
+          double* dst = P.nb_sums + ((long long)nb_img * P.n_out + nb_c0 + lane) * 2;
+          atomicAdd(dst, (double)nb_s1);
+          atomicAdd(dst + 1, (double)nb_s2);
+        }
+        nb_s1 = 0.f;
+        nb_s2 = 0.f;
         nb_img = t.img;
         nb_c0 = c0;
-      }
-      if (nb && c0 + lane < P.n_out && nb_fresh) {
-        nb_fresh = false;
-        const int c = c0 + lane;
+        const int c = min(c0 + lane, P.n_out - 1);
         const int ncpg = P.n_out / P.nb_groups;
         const double cnt = (double)P.H * P.W * ncpg;
         const double* st = P.nb_stats + ((long long)t.img * P.nb_groups + c / ncpg) * 2;
@@ -414,17 +414,42 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&res_bar[e], res_par);
           res_par ^= 1;
           if (nb) {
-            // v = dL/d act(norm(x)); accumulate pass 1 of the norm backward: sum du, sum du*xhat over the pixels
-            const int hrow0 = t.h0 + k * rows_per_chunk;
+            // v = dL/d act(norm(x)); accumulate pass 1 of the norm backward: sum du, sum du*xhat over the pixels.
+            // Pixels outside the image are zeroed up front (their x tile is zero-filled), the activation is chosen
+            // outside the element loop, two partial sums break the dependency chains.
+            if (!interior) {
+              const int hrow0 = t.h0 + k * rows_per_chunk;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
-              const bool ok = interior || ((hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W));
-              const float xh = (x - nb_mean) * nb_rstd;
-              const float du = ok ? v[i] * act_grad_fast(fmaf(xh, nb_ga, nb_be), P.nb_act) : 0.f;
-              nb_s1 += du;
-              nb_s2 = fmaf(du, xh, nb_s2);
+              for (int i = 0; i < 32; ++i)
+                if (!((hrow0 + (i >> tw_shift) < P.H) && (t.w0 + (i & (P.TW - 1)) < P.W))) v[i] = 0.f;
             }
+            float s1b = 0.f, s2b = 0.f;
+            if (P.nb_act == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float x0 = *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+                const float x1 = *reinterpret_cast<const float*>(my_res + swz(i + 1, lane >> 2) + ((lane & 3) << 2));
+                const float xh0 = (x0 - nb_mean) * nb_rstd, xh1 = (x1 - nb_mean) * nb_rstd;
+                const float du0 = v[i] * act_grad_fast(fmaf(xh0, nb_ga, nb_be), 1);
+                const float du1 = v[i + 1] * act_grad_fast(fmaf(xh1, nb_ga, nb_be), 1);
+                nb_s1 += du0; s1b += du1;
+                nb_s2 = fmaf(du0, xh0, nb_s2); s2b = fmaf(du1, xh1, s2b);
+              }
+            } else {
+              const int a = P.nb_act;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float x0 = *reinterpret_cast<const float*>(my_res + swz(i, lane >> 2) + ((lane & 3) << 2));
+                const float x1 = *reinterpret_cast<const float*>(my_res + swz(i + 1, lane >> 2) + ((lane & 3) << 2));
+                const float xh0 = (x0 - nb_mean) * nb_rstd, xh1 = (x1 - nb_mean) * nb_rstd;
+                const float du0 = v[i] * ((a == 2 && fmaf(xh0, nb_ga, nb_be) <= 0.f) ? 0.2f : 1.0f);
+                const float du1 = v[i + 1] * ((a == 2 && fmaf(xh1, nb_ga, nb_be) <= 0.f) ? 0.2f : 1.0f);
+                nb_s1 += du0; s1b += du1;
+                nb_s2 = fmaf(du0, xh0, nb_s2); s2b = fmaf(du1, xh1, s2b);
+              }
+            }
+            nb_s1 += s1b;
+            nb_s2 += s2b;
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)  // row = pixel i, word = this lane's channel: conflict-free
@@ -494,7 +519,11 @@ tapgemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         ap ^= 1;
       }
     }
-    if (nb) nb_flush();
+    if (nb && nb_img >= 0 && nb_c0 + lane < P.n_out) {
+      double* dst = P.nb_sums + ((long long)nb_img * P.n_out + nb_c0 + lane) * 2;
+      atomicAdd(dst, (double)nb_s1);
+      atomicAdd(dst + 1, (double)nb_s2);
+    }
     if (lane == 0) tma_store_wait_read<0>();
   }
 

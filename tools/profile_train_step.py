@@ -56,6 +56,13 @@ if args.events:
     rows = sorted(((a.elapsed_time(b), shape, algo) for algo, issued, a, b, shape in rec), key=lambda r: -r[0])[:25]
     for t, shape, algo in rows:
         print(f"   {t:7.3f} ms {algo / t / 1e9:8.1f} TF/s {shape}")
+    agg = {}
+    for algo, issued, a, b, shape in rec:
+        e = agg.setdefault(tuple(shape), [0, 0.0])
+        e[0] += 1; e[1] += a.elapsed_time(b)
+    print("by shape (count, total ms):")
+    for shape, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        print(f"   {n:4d} {t:8.3f} ms  {shape}")
     ops.profile_tapgemm(False)
 else:
     torch.cuda.cudart().cudaProfilerStart()
