@@ -303,17 +303,41 @@ class NormConvOutL(Layer):
         x, st, a, N, H, W = self.saved[-1]
         G.wgrad("k3", self._dy_planes(dy_nchw_or_nhwc), a, gw, n=N)
 
+    def wgrad_pair(self, dy1, dy2):
+        """the conv's weight gradients for two output gradients in ONE launch (NCHW path, Cout <= 8: the two are
+        stacked along the output channels, 8 apart) -> (gw1, gw2), each shaped like the conv's gradient buffer"""
+        x, st, a, N, H, W = self.saved[-1]
+        cp = self.cp(self.conv)
+        taps, co_p, ci_p = cp.gw.shape
+        if not self.nchw or co_p != 8:
+            g1, g2 = torch.zeros_like(cp.gw), torch.zeros_like(cp.gw)
+            self.wgrad_only(dy1, g1)
+            self.wgrad_only(dy2, g2)
+            return g1, g2
+        Cc = dy1.shape[1]
+        both = torch.zeros((N, 16, H, W), dtype=torch.float32, device=dy1.device)
+        both[:, :Cc] = dy1
+        both[:, 8:8 + Cc] = dy2
+        gw2 = torch.zeros((taps, 16, ci_p), dtype=torch.float32, device=dy1.device)
+        G.wgrad("k3", ops.nchw_to_planes(both, c_pad=16), a, gw2, n=N)
+        return gw2[:, :8].contiguous(), gw2[:, 8:].contiguous()
+
     def _dy_planes(self, dy):
         return ops.nchw_to_planes(dy) if self.nchw else ops.f32_to_planes(dy, CVT_PLAIN)
 
-    def bwd(self, dy):
+    def bwd(self, dy, gw_known=None):
+        """``gw_known``: the conv's weight gradient for ``dy`` when the caller already has it (the trainer: by
+        linearity from the adaptive weight's two gradients) -- it is added instead of being recomputed"""
         x, st, a, N, H, W = self.saved.pop()
         cp = self.cp(self.conv)
         dyp = self._dy_planes(dy)
         if cp.gb is not None:
             g2 = ops.nchw_to_nhwc(dy) if self.nchw else dy
             ops.colsum_(cp.gb[:cp.co], g2.reshape(-1, cp.co))
-        G.wgrad("k3", dyp, a, cp.gw, n=N)
+        if gw_known is not None:
+            cp.gw.add_(gw_known)
+        else:
+            G.wgrad("k3", dyp, a, cp.gw, n=N)
         self.tr.done(self.conv)
         # pass 1 of the norm backward (sum du, sum du*xhat) rides in the data-gradient conv's epilogue where it can
         nb = ops.nb_context(x, st, self.norm.weight.detach(), self.norm.bias.detach(), act="swish", groups=32,
@@ -779,9 +803,10 @@ class VQGANTrainer:
         xrec = self.dec_out.fwd(self.dec_body.fwd(self.dec_in.fwd(Act(q, stq))))
         return xrec, r["sqerr"], z.numel()
 
-    def gen_backward(self, dxrec, cb_scale):
-        """dxrec fp32 NCHW (already multiplied by the loss scale); cb_scale = loss scale x d(loss)/d(codebook_loss)"""
-        g = self.dec_in.bwd(self.dec_body.bwd(self.dec_out.bwd(dxrec)))
+    def gen_backward(self, dxrec, cb_scale, conv_out_gw=None):
+        """dxrec fp32 NCHW (already multiplied by the loss scale); cb_scale = loss scale x d(loss)/d(codebook_loss);
+        conv_out_gw: decoder.conv_out's weight gradient for dxrec if already known"""
+        g = self.dec_in.bwd(self.dec_body.bwd(self.dec_out.bwd(dxrec, gw_known=conv_out_gw)))
         g = self.pqconv.bwd(g)
         z, idx, ids = self._vq
         nel = z.numel()
@@ -814,14 +839,12 @@ class VQGANTrainer:
         self.dnet.bwd(d_lf, want_params=False, want_input=True, dx_out=d_xr)
         g_g = ops.diffaug_bwd(d_xr, r, t) if self.diff_aug else d_xr
         # adaptive weight from the two gradients wrt decoder.conv_out.weight (vqgan_loss.py:5-12)
-        co = self.gen.convs[self.model.decoder.conv_out]
-        rg, gg = torch.zeros_like(co.gw), torch.zeros_like(co.gw)
-        self.dec_out.wgrad_only(g_nll, rg)
-        self.dec_out.wgrad_only(g_g, gg)
+        rg, gg = self.dec_out.wgrad_pair(g_nll, g_g)
         ops.adaptive_weight(rg, gg, dw, 1.0 / S, self.disc_weight_max, 1.0 if step >= self.disc_start_step else 0.0)
         dxrec = ops.axpy_dev(g_nll, g_g, dw)                 # loss = nll + d_weight * g_loss + codebook_loss
         self._arm(self.gen, last)
-        self.gen_backward(dxrec, S)
+        # conv_out's weight gradient is linear in dxrec: rg + d_weight * gg, no third weight-gradient launch
+        self.gen_backward(dxrec, S, conv_out_gw=ops.axpy_dev(rg, gg, dw))
         self._reduce = False
         out = dict(acc=acc, dw=dw, nel=nel, n_logit=logits_fake.numel(), sqerr=sqerr, z_numel=z_numel)
         # ---- discriminator update (step > disc_start_step, vqgan_model.py:475-486)
