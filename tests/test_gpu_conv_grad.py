@@ -248,7 +248,8 @@ def test_sample_step_draws_the_categorical_law(cuda):
     assert torch.equal(xa, xb) and not torch.equal(xa, xc)
 
 
-@pytest.mark.parametrize("N,H,W,C,act", [(2, 64, 32, 128, "swish"), (1, 40, 24, 256, "swish"), (2, 32, 16, 128, "lrelu")])
+@pytest.mark.parametrize("N,H,W,C,act", [(2, 64, 32, 128, "swish"), (1, 40, 24, 256, "swish"), (2, 32, 16, 128, "lrelu"),
+                                         (8, 32, 16, 512, "swish"), (3, 128, 64, 256, "swish"), (2, 256, 128, 128, "swish")])
 def test_norm_backward_sums_fused_into_the_data_gradient_conv(cuda, N, H, W, C, act):
     """t2h_tapgemm_params.nb_sums: pass 1 of the GroupNorm backward (sum du, sum du*xhat per image and channel)
     accumulated in the epilogue of the 3x3 data-gradient conv that produces dy, against the stand-alone reduce pass of

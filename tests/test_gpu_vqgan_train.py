@@ -187,3 +187,42 @@ def test_micro_batches_adam_and_resume(cuda, tmp_path):
     # the mirrors' state_dict still has the reference's keys / shapes after flattening
     sd = m.decoder.state_dict()
     assert sd["conv_out.weight"].shape == (3, cfg["dec"]["ch"], 3, 3)
+
+
+def test_training_step_with_and_without_the_fused_norm_backward_sums(cuda):
+    """Channel counts at which the data-gradient convs run on the swapped kernel (128 / 256, as BASELINE config 5's
+    levels): the whole training step with pass 1 of the norm backward in the conv epilogues (ops.nb_context, the
+    default) against the same step with the stand-alone reduce launches -- every generator / discriminator gradient
+    and the losses; the two differ only in fp32 summation order."""
+    from text2human_b200 import ops
+    from text2human_b200.vqgan_train import VQGANTrainer
+    cfg = dict(enc=dict(ch=128, num_res_blocks=1, attn_resolutions=[16], in_channels=3, resolution=64, z_channels=64,
+                        ch_mult=[1, 2, 2], double_z=False, dropout=0.0),
+               n_embed=64, embed_dim=64, ndf=16, disc_layers=3, disc_start_step=0, step=5, batch=2)
+    ops.set_precision("fp32")
+    grads, losses, launches = [], [], []
+    for on in (True, False):
+        old = ops.FUSE_NB["on"]
+        ops.FUSE_NB["on"] = on
+        try:
+            m, disc, _ = build(cuda, cfg)
+            tr = VQGANTrainer(m, disc, disc_start_step=0, disc_weight_max=1.0)
+            tr.aug_draw_fn = recorded_draws(R.VQGAN_TRAIN_AUG_SEED)
+            data = dict(image=R.image(107, 2, 3, 64, 32), texture_mask=R.blocky_mask(108, 2, 64, 32, 8))
+            l0 = ops.COUNTERS["launches"]
+            tr.training_step(data, 5)
+            torch.cuda.synchronize()
+            launches.append(ops.COUNTERS["launches"] - l0)
+            losses.append(tr.losses())
+            grads.append((tr.gen.flat_g.clone(), tr.dsc.flat_g.clone()))
+        finally:
+            ops.FUSE_NB["on"] = old
+    assert launches[0] < launches[1]          # reduce launches (and their memsets) are gone where the fusion applies
+    for k in losses[0]:
+        assert abs(losses[0][k] - losses[1][k]) <= 1e-5 * max(1.0, abs(losses[1][k])), k
+    for a, b in zip(grads[0], grads[1]):
+        e = float((a - b).abs().max() / b.abs().max())
+        assert e < 2e-5, e
+    print(f"[nb] training step launches {launches[0]} fused vs {launches[1]}; generator / discriminator gradient "
+          f"difference {float((grads[0][0] - grads[1][0]).abs().max() / grads[1][0].abs().max()):.1e} / "
+          f"{float((grads[0][1] - grads[1][1]).abs().max() / grads[1][1].abs().max()):.1e}")
