@@ -141,3 +141,32 @@ def test_conv_data_gradient_is_a_forward_conv_with_flipped_transposed_weights():
         got = F.conv2d(dy, wd, padding=k // 2)
         assert (got - x.grad).abs().max() <= 1e-4 * x.grad.abs().max()
         assert ops.pack_conv_weight(wd, 2).shape == (2, k * k, cin, (cout + 7) // 8 * 8)
+
+
+def test_fusion_gates_choose_the_kernels_shape_constraints():
+    """which launches the host logic hands to the fused kernels: t2h_attn_fwd needs head_dim 64 and 128..512 tokens
+    in multiples of 128 (the score rows of a query block fill tensor memory); the norm-backward sums ride only on
+    data-gradient convs the swapped-operand kernel runs (channels % 128, more than one image row)"""
+    import torch
+    from text2human_b200 import ops
+    assert ops.can_fuse_attn(512, 64) and ops.can_fuse_attn(128, 64) and ops.can_fuse_attn(384, 64)
+    assert not ops.can_fuse_attn(640, 64) and not ops.can_fuse_attn(64, 64) and not ops.can_fuse_attn(192, 64)
+    assert not ops.can_fuse_attn(512, 128) and not ops.can_fuse_attn(512, 32)
+    old = ops.set_fused_attn(False)
+    try:
+        assert not ops.can_fuse_attn(512, 64)
+    finally:
+        ops.set_fused_attn(old)
+    gamma, beta = torch.ones(128), torch.zeros(128)
+    st = torch.zeros(2, 32, 2, dtype=torch.float64)
+    ctx = ops.nb_context(torch.zeros(2, 8, 4, 128), st, gamma, beta, act="swish", groups=32, eps=1e-6)
+    assert ctx is not None and ctx["sums"].shape == (2 * 128 * 2,) and ctx["sums"].dtype == torch.float64
+    assert float(ctx["sums"].abs().sum()) == 0.0            # the epilogue accumulates into it
+    assert ops.nb_context(torch.zeros(2, 8, 4, 64), st, gamma[:64], beta[:64], act="swish", groups=32, eps=1e-6) is None
+    assert ops.nb_context(torch.zeros(2, 1, 4, 128), st, gamma, beta, act="swish", groups=32, eps=1e-6) is None
+    old_nb = ops.FUSE_NB["on"]
+    ops.FUSE_NB["on"] = False
+    try:
+        assert ops.nb_context(torch.zeros(2, 8, 4, 128), st, gamma, beta, act="swish", groups=32, eps=1e-6) is None
+    finally:
+        ops.FUSE_NB["on"] = old_nb
