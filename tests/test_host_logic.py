@@ -170,3 +170,31 @@ def test_fusion_gates_choose_the_kernels_shape_constraints():
         assert ops.nb_context(torch.zeros(2, 8, 4, 128), st, gamma, beta, act="swish", groups=32, eps=1e-6) is None
     finally:
         ops.FUSE_NB["on"] = old_nb
+
+
+def test_branch_free_gelu_constants_reproduce_erf_gelu():
+    """the tap-GEMM epilogue's GELU (csrc/t2h_ptx.cuh:gelu_erf, Abramowitz & Stegun 7.1.26 evaluated through erfc):
+    the constants as written in the kernel source, restated in float32 numpy, against torch's exact-erf nn.GELU
+    (transformer_arch.py:85) over [-8, 8] -- the absolute error must stay at the fp32 formula's own level"""
+    import os
+    import re
+    import numpy as np
+    import torch
+    src = open(os.path.join(os.path.dirname(__file__), "..", "text2human_b200", "csrc", "t2h_ptx.cuh")).read()
+    body = src[src.index("__device__ __forceinline__ float gelu_erf(float x)"):]
+    body = body[:body.index("\n}\n")]
+    nums = [float(v) for v in re.findall(r"(-?\d+\.\d+)f", body)]
+    # sqrt(1/2), p, 1, a5, a4, a3, a2, a1, log2(e), 0.5, 2
+    inv_sqrt2, p, one, a5, a4, a3, a2, a1, log2e = nums[:9]
+    assert abs(inv_sqrt2 - 2 ** -0.5) < 1e-9 and one == 1.0 and abs(log2e - 1.4426950408889634) < 1e-9
+    f = np.float32
+    x = np.linspace(-8, 8, 400001).astype(np.float32)
+    z = np.abs(x) * f(inv_sqrt2)
+    t = f(1) / (f(p) * z + f(1))
+    poly = ((((f(a5) * t + f(a4)) * t + f(a3)) * t + f(a2)) * t + f(a1))
+    e = np.exp2((-(z * z)) * f(log2e)).astype(np.float32)
+    c = poly * t * e
+    got = (f(0.5) * x * np.where(x >= 0, f(2) - c, c)).astype(np.float32)
+    ref = torch.nn.functional.gelu(torch.from_numpy(x).double()).numpy()
+    assert np.abs(got - ref).max() < 6e-7
+    assert np.abs(got[np.abs(x) < 1] - ref[np.abs(x) < 1]).max() < 2e-7
